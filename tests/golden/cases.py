@@ -1,0 +1,53 @@
+"""Seeded inputs shared by ``make_golden.py`` (which runs the verbatim reference on them) and the tests."""
+
+from __future__ import annotations
+
+import torch
+
+from oracle import weights
+
+PROCESSOR_CASES = [
+    dict(name="split_d40_l3", kind="split", c=320, n=64, b=2, gates=(0.1, 0.9), delta_scale=3.0, seed=11),
+    dict(name="split_d40_l0", kind="split", c=320, n=64, b=2, gates=(0.1, 0.9), delta_scale=0.0, seed=12),
+    dict(name="split_d80_l1", kind="split", c=640, n=48, b=1, gates=(0.9, 0.1), delta_scale=1.0, seed=13),
+    dict(name="split_d160_l3", kind="split", c=1280, n=16, b=2, gates=(0.5, 0.5), delta_scale=3.0, seed=14),
+    dict(name="base_d40_both", kind="base", c=320, n=64, b=2, mode="both", seed=15),
+    dict(name="base_d80_img", kind="base", c=640, n=32, b=1, mode="image_dominant", seed=16),
+    dict(name="base_d160_aoe", kind="base", c=1280, n=16, b=1, mode="aoe_dominant", seed=17),
+]
+
+
+def processor_inputs(case):
+    g = torch.Generator().manual_seed(case["seed"])
+    it = weights._Init(case["seed"] + 1000, 1.7, 0.0)     # gain > 1 so the softmaxes are not flat
+    c = case["c"]
+    it.linear("to_q", c, c, bias=False)
+    it.linear("to_k", 768, c, bias=False)
+    it.linear("to_v", 768, c, bias=False)
+    it.linear("to_out.0", c, c)
+    if case["kind"] == "split":
+        it.linear("processor.to_k_dis", 768, c, bias=False)
+        it.linear("processor.to_v_dis", 768, c, bias=False)
+        it.sd["processor.anat_gate"] = torch.tensor(float(case["gates"][0]))
+        it.sd["processor.dis_gate"] = torch.tensor(float(case["gates"][1]))
+    x = 2.0 * torch.randn(case["b"], case["n"], c, generator=g)
+    tokens = 48 if case["kind"] == "split" else 32
+    ehs = 2.0 * torch.randn(case["b"], tokens, 768, generator=g)
+    return it.sd, x, ehs
+
+
+def cross_attention_processor_names():
+    return [f"{p}.transformer_blocks.0.attn2.processor" for p, _ in weights.attention_sites()]
+
+
+def purifier_inputs():
+    g = torch.Generator().manual_seed(21)
+    w = weights.make_purifier_state(seed=22)
+    return w, torch.randn(3, 16, 768, generator=g), torch.randn(3, 16, 768, generator=g)
+
+
+def aoe_inputs():
+    w = weights.make_aoe_state(seed=23)
+    labels = torch.cat([torch.linspace(0, 3, 13), torch.tensor([-0.5, 3.7, 2.999, 1.0])])
+    src = torch.full_like(labels, 2.0)
+    return w, labels, src
