@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Headline benchmark: DADD patient-conditioned progression (13 MES levels x 50 DDIM steps, lambda = 3, 256x256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--patients P] [--impl b200|reference]
+
+One "step" = one progression batch per GPU: P patients x 13 levels go through conditioning (AOE + purifier), 50
+CUDA-graph-replayed denoising steps (UNet + fused DDIM) and the VAE decode, producing P*13 images of 256x256.
+Prints ONE JSON line (rank 0).  ``value``: images/s with inputs resident in HBM, timed with CUDA events over exactly K
+steps (max over ranks).  ``e2e``: the same through the public API ``sample_progressions`` with pinned HOST inputs and a
+device->host read of the finished images inside the timed region.  ``--impl reference`` times the reference's CPU path
+(the oracle port: same graph, PyTorch eager fp32 - diffusers is not installable here) on the box's host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LEVELS, DDIM_STEPS, STEER = 13, 50, 3.0
+UNET_GFLOP_PER_SAMPLE_STEP = 178.7
+SELF_ATTN_N, SELF_ATTN_D, SELF_ATTN_H = 1024, 40, 8
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_sample(batch: int, seed: int = 0):
+    """A bounded sample of the reference CPU path: ONE UNet denoising step at B = 13 (of the 50) through the oracle
+    port, plus ONE VAE decode at B = 13; returns (seconds_unet_step, seconds_decode, cores)."""
+    import torch
+    from oracle import conditioning, unet as ounet, weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = weights.make_module_state(seed=seed)
+    uw, aw, pw, vw = (weights.sub_state(state, p) for p in ("unet.unet.", "ordinal_embedder.", "feature_purifier.", "vae.vae."))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 32, 32, generator=g).repeat(batch, 1, 1, 1)
+    img = torch.randn(1, 16, 768, generator=g).expand(batch, -1, -1).contiguous()
+    tgt, src = torch.linspace(0, 3, batch), torch.zeros(batch)
+    t = torch.full((batch,), 999, dtype=torch.long)
+    with torch.no_grad():
+        cond = conditioning.prepare_conditioning(aw, pw, tgt, src, img)
+
+        def unet_step():
+            t0 = time.perf_counter()
+            ounet.unet_forward(uw, x, t, cond, ounet.CrossCfg(True, STEER))
+            return time.perf_counter() - t0
+
+        def decode():
+            t0 = time.perf_counter()
+            ounet.latents_to_images(vw, x)
+            return time.perf_counter() - t0
+        return unet_step, decode, torch.get_num_threads()
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    unet_step, decode, cores = cpu_reference_sample(LEVELS)
+    unet_step()                                                   # one untimed pass (each is ~10 s of host work)
+    with torch.no_grad():
+        t_unet = [unet_step() for _ in range(args.steps)]
+        t_dec = decode()
+    per_step = statistics.mean(t_unet)
+    progression_s = DDIM_STEPS * per_step + t_dec
+    value = LEVELS / progression_s
+    sample = (f"{args.steps} timed UNet denoising step(s) at B=13 (oracle port, fp32 eager, {cores} threads) + 1 VAE decode at "
+              f"B=13; one 13x50 progression extrapolated as 50 x step + decode = {progression_s:.1f} s")
+    print(json.dumps({
+        "impl": "reference", "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": progression_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "13 MES levels x 50 DDIM steps, lambda=3, 256x256, SD-1.x-shaped random-init weights",
+                   "patients_per_gpu": 1, "levels": LEVELS, "ddim_steps": DDIM_STEPS},
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args) -> None:
+    import torch
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200 import _lib, ops, parallel
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import (_latents_to_images, _sample, _build_labels,
+                                                                         sample_progressions)
+
+    rank, local, world = parallel.init_from_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pk = peaks()
+    patients, batch = args.patients, args.patients * LEVELS
+
+    torch.manual_seed(0)                                          # random-init SD-1.x-shaped weights (PyTorch default inits)
+    module = P.DiffusionModuleWithIP(P.default_config())
+    module.to(dev).eval()
+
+    g = torch.Generator().manual_seed(100 + rank)
+    host_tokens = torch.randn(patients, 16, 768, generator=g).pin_memory()
+    host_source = torch.zeros(patients).pin_memory()
+    host_noise = torch.randn(patients, 4, 32, 32, generator=g).pin_memory()
+    host_images = torch.empty(batch, 3, 256, 256, dtype=torch.float32).pin_memory()
+    d_tokens = host_tokens.to(dev).repeat_interleave(LEVELS, 0)
+    d_source = host_source.to(dev).repeat_interleave(LEVELS)
+    d_target = _build_labels(LEVELS, 0.0, 3.0, dev).repeat(patients)
+    d_noise = host_noise.to(dev).repeat_interleave(LEVELS, 0)
+
+    def step_resident():
+        lat = _sample(module, d_target, d_source, d_tokens, d_noise, DDIM_STEPS, dev, 0.0, 1.0, None, STEER, 1.0, False, True)
+        return _latents_to_images(module, lat)
+
+    def step_e2e():
+        imgs = sample_progressions(module, host_tokens, host_source, LEVELS, DDIM_STEPS, dev, steer_scale=STEER,
+                                   init_latents=host_noise)
+        host_images.copy_(imgs, non_blocking=True)
+
+    def timed(fn, steps):
+        parallel.barrier()
+        torch.cuda.synchronize(dev)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            fn()
+        end.record()
+        torch.cuda.synchronize(dev)
+        parallel.barrier()
+        return parallel.max_over_ranks(start.elapsed_time(end) / 1e3, dev)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        step_e2e()
+        torch.cuda.synchronize(dev)
+        eng = next(iter(module.__dict__["_b200_engines"].values()))
+        sampler = ClockSampler(local).start() if rank == 0 else None
+        _lib.reset_launch_count()
+        seconds = timed(step_resident, args.steps)
+        eager_launches = _lib.launch_count()
+        seconds_e2e = timed(step_e2e, args.steps)
+        clocks = sampler.stop() if sampler else None
+
+        # ---- dominant kernel, timed live on the launching stream: self-attention N=1024, d=40 at this batch ----
+        c = SELF_ATTN_H * SELF_ATTN_D
+        qkv = torch.randn(batch, SELF_ATTN_N, 3 * c, device=dev, dtype=torch.bfloat16)
+        reps = 20
+        for _ in range(3):
+            ops.self_attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], SELF_ATTN_H)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            ops.self_attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], SELF_ATTN_H)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        attn_s = e0.elapsed_time(e1) / 1e3 / reps
+        attn_flop = 4.0 * SELF_ATTN_N * SELF_ATTN_N * c * batch
+        # ---- GroupNorm+SiLU 320ch @32x32 (the most frequent memory-bound kernel) ----
+        xg = torch.randn(batch, 320, 32, 32, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gam, bet = torch.ones(320, device=dev), torch.zeros(320, device=dev)
+        for _ in range(3):
+            ops.group_norm(xg, gam, bet, 32, 1e-5, True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            ops.group_norm(xg, gam, bet, 32, 1e-5, True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        gn_s = e0.elapsed_time(e1) / 1e3 / reps
+        gn_bytes = xg.numel() * 2 * 2
+
+    images_total = batch * world * args.steps
+    value = images_total / seconds
+    e2e_value = images_total / seconds_e2e
+    launches = eager_launches + args.steps * DDIM_STEPS * eng.launches_per_step
+    if rank != 0:
+        return
+    unet_step, decode, cores = cpu_reference_sample(LEVELS)
+    unet_step()
+    t_unet, t_dec = unet_step(), decode()
+    cpu_progression = DDIM_STEPS * t_unet + t_dec
+    tflops = batch * world * args.steps * DDIM_STEPS * UNET_GFLOP_PER_SAMPLE_STEP / 1e3 / seconds
+    print(json.dumps({
+        "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": seconds / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "13 MES levels x 50 DDIM steps, lambda=3, 256x256, SD-1.x-shaped random-init weights, "
+                               "CFG off (routing gates), eta=0, VAE decode included",
+                   "patients_per_gpu": patients, "levels": LEVELS, "ddim_steps": DDIM_STEPS, "images_per_step_per_gpu": batch,
+                   "parallelism": f"independent (patient x level) units, {world} rank(s), no data-path collective",
+                   "l2": "inputs larger than L2: 1.8 GB of bf16 weights stream through the 126 MB L2 on every UNet pass"},
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(host_tokens.numel() * 4 + host_source.numel() * 4 + host_noise.numel() * 4),
+                "d2h_bytes_per_step": int(host_images.numel() * 4), "ms_per_step": seconds_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "dadd_launches_per_denoising_step": int(eng.launches_per_step),
+        "unet_tflops_achieved": tflops, "unet_frac_of_sustained_bf16_peak": tflops / pk["bf16_tflops_sustained"] / world,
+        "clocks": clocks,
+        "roofline": {"kernel": "self_attn (N=1024, d=40, H=8) at the bench batch", "bound": "tensor",
+                     "achieved": attn_flop / attn_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": attn_flop / attn_s / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                     "us_per_launch": attn_s * 1e6},
+        "roofline_groupnorm": {"kernel": "groupnorm+silu NHWC 320ch 32x32 at the bench batch", "bound": "hbm",
+                               "achieved": gn_bytes / gn_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": gn_bytes / gn_s / 1e9 / pk["hbm_gbs"], "traffic": None, "us_per_launch": gn_s * 1e6},
+        "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
+                         "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
+                                   f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},
+    }))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--patients", type=int, default=8, help="patient progressions per GPU per step (13 images each)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

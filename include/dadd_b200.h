@@ -1,0 +1,141 @@
+/*
+ * dadd_b200.h - C ABI of the B200 (sm_100a) kernels behind DADD's UNet-denoising hot path.
+ *
+ * The reference (umutdundar99/progressive-stable-diffusion) is pure Python and has no FFI; each entry
+ * point below names the reference code it replaces (file:line relative to the reference tree).
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless marked "host";
+ *   - buffers are borrowed: they must stay alive until the work queued on `stream` has run;
+ *   - work is queued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream), nothing
+ *     synchronises, so every call is CUDA-graph capturable;
+ *   - return 0 on success, non-zero on error (never throws); dadd_last_error() returns the message of the
+ *     calling thread's last failure;
+ *   - dtype codes: DADD_F32 = 0, DADD_BF16 = 1.
+ */
+#ifndef DADD_B200_H
+#define DADD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DADD_F32 0
+#define DADD_BF16 1
+
+#define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
+#define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
+
+/* ABI version of this header (bumped on any signature change). */
+int dadd_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* dadd_last_error(void);
+/* Number of kernels launched by this library since load / since the last reset (all threads). */
+int64_t dadd_launch_count(void);
+void dadd_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * DDIM update fused with the optional classifier-free-guidance combine.
+ * Replaces src/pipelines/inference/inference_pipeline_ip.py:427-430 (CFG) and :434-468 (x0, clamp, update)
+ * and the copies at src/pipelines/evaluation/evaluation_pipeline.py:537-562.
+ *   eps  = eps_uncond ? eps_uncond + guidance * (eps_cond - eps_uncond) : eps_cond
+ *   x0   = clamp((x - sqrt_1mab_t * eps) / sqrt_ab_t, -clamp, +clamp)
+ *   x    = is_last ? x0 : sqrt_ab_prev * x0 + eps_coef * eps (+ sigma * noise when noise != NULL)
+ * Every operation is a separately rounded fp32 op (no FMA contraction): bit-exact with the reference's
+ * eager fp32 tensor arithmetic.  x is updated in place.  eps_dtype applies to eps_cond and eps_uncond.
+ */
+int dadd_ddim_step(float* x, const void* eps_cond, const void* eps_uncond /* nullable */, int eps_dtype,
+                   float guidance, float sqrt_ab_t, float sqrt_1mab_t, float sqrt_ab_prev, float eps_coef,
+                   float sigma, const float* noise /* nullable */, float clamp, int is_last, int64_t n,
+                   void* stream);
+
+/* Same update with the per-step scalars read on the device, so that one captured CUDA graph can be replayed
+ * for every step of the schedule.  coef_table is [n_steps][8] fp32 rows
+ *   {sqrt_ab_t, sqrt_1mab_t, sqrt_ab_prev, eps_coef, sigma, is_last (0/1), 0, 0}
+ * and step_state is int32[2] = {current step, next step} maintained by dadd_step_begin(). */
+int dadd_ddim_step_table(float* x, const void* eps_cond, const void* eps_uncond /* nullable */, int eps_dtype,
+                         float guidance, const float* coef_table, const int32_t* step_state,
+                         const float* noise /* nullable; [n_steps][n] when given */, float clamp, int64_t n,
+                         void* stream);
+
+/* First node of a per-step graph: step_state[0] = step_state[1]; step_state[1] += 1; and copy row
+ * step_state[0] of a [n_steps][row_len] table (the hoisted per-step time-embedding projections of all
+ * resnets) into `row_out`.  `table` may be NULL (row_len = 0). */
+int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64_t row_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional per-(sample,channel) additive term, + optional SiLU).
+ * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, conv_norm_out + conv_act and
+ * Transformer2DModel.norm reached through src/models/unet/unet.py:140-146:
+ *   y = act(GroupNorm_G(x + chan_add[b * chan_add_stride + c]; eps) * gamma[c] + beta[c]),  act = SiLU or identity.
+ * Statistics in fp32 (shifted sums + Chan combine).  x/y: `dtype`; gamma/beta/chan_add: fp32.
+ * C % G == 0 and C % 8 == 0 required; for NHWC additionally (C/8) <= 512.
+ */
+int dadd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* chan_add /* nullable */,
+                       int64_t chan_add_stride /* elements between samples */, void* y, int B, int C, int HW, int G, float eps, int apply_silu, int layout, int dtype,
+                       void* stream);
+
+/* LayerNorm over the last dimension (the 48 LayerNorms of the BasicTransformerBlocks and the three of
+ * src/models/feature_purifier.py:46-47,62).  x,y: [rows][C] `dtype`; gamma/beta fp32; C % 8 == 0, C <= 2048. */
+int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps,
+                       int dtype, void* stream);
+
+/* GEGLU gate of the transformer feed-forward: y[r][j] = x[r][j] * gelu_erf(x[r][inner + j]), x: [rows][2*inner]. */
+int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-pathway cross-attention core.
+ * Replaces the three explicit matmul/softmax/matmul pathways and the gate merge of
+ * SplitInjectionAttentionProcessor.__call__ (src/models/attention_processor_routing_gates.py:148-178) and, with
+ * n_seg = 1, seg_len = 32, the single softmax of OrdinalIPAttnProcessor2_0.__call__
+ * (src/models/attention_processor_base.py:96-118):
+ *   o[b][n][h*d + :] = sum_s gates[s] * softmax(q_bh[n] . k_s^T * scale) v_s ,  s over n_seg segments of seg_len tokens
+ * q: bf16 [B][N][*] with row stride q_stride elements, head h at column h*d (i.e. the to_q output as is);
+ * k_cat, v_cat: bf16 [B][H][n_seg*seg_len][d] (step-invariant; projected once per sampling call, token order
+ * dis | anat | delta = encoder_hidden_states[:, :16], [:, 16:32], [:, -16:], routing_gates.py:129-131);
+ * gates: fp32[n_seg] ON DEVICE in token order (dis_gate, anat_gate, delta_scale);
+ * o: bf16 [B][N][*] with row stride o_stride, written at column h*d (heads merged, ready for to_out).
+ * d in {40, 80, 160} (d % 8 == 0, d <= 160); seg_len % 16 == 0; n_seg*seg_len <= 64.
+ * delta_scale == 0 must be expressed as n_seg = 2 (the pathway is skipped, routing_gates.py:160,177).
+ */
+int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
+                        int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg, const float* gates,
+                        float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Self-attention core (attn1): o = softmax(q k^T * scale) v per (b, h), no mask.
+ * Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0, installed by
+ * src/models/attention_processor_routing_gates.py:284-286 and attention_processor_base.py:196-197.
+ * q, k, v: bf16 [B][N][*] with row strides (elements); head h at column h*d (so the three can alias one
+ * fused [B][N][3C] projection output); o: bf16, same convention.  d in {40, 64, 80, 128, 160} (d % 8 == 0).
+ */
+int dadd_self_attn_fwd(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride,
+                       int64_t v_stride, void* o, int64_t o_stride, int B, int H, int N, int d, float scale,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Feature Purifier pieces (src/models/feature_purifier.py:81-95), fp32 (runs once per sampling call).
+ * (1) multi-head attention core of nn.MultiheadAttention(768, 8): q [B][Lq][D], k,v [B][Lk][D] (already
+ *     in-projected), o [B][Lq][D] (before out_proj); Lq, Lk <= 32, D/heads <= 128.
+ * (2) gating epilogue: y = LayerNorm(img - sigmoid(gate_logits) * disease; gamma, beta, eps), all [rows][D].
+ */
+int dadd_purifier_attn_fwd(const float* q, const float* k, const float* v, float* o, int B, int Lq, int Lk, int D,
+                           int heads, void* stream);
+int dadd_purifier_gate_ln_fwd(const float* img, const float* gate_logits, const float* disease, const float* gamma,
+                              const float* beta, float* y, int64_t rows, int D, float eps, void* stream);
+
+/* AOE table lookup (src/models/ordinal_embedder.py:107-127,155-171,15-40): table E[k] = base + cumsum(deltas)[k-1],
+ * labels clamped to [0, K-1], lo = floor, hi = min(lo+1, K-1), out[b] = E[lo]*(1-a) + E[hi]*a, a = y - lo.
+ * base [D], deltas [K-1][D], labels [B], out [B][D], all fp32.  Integer indices are exact. */
+int dadd_aoe_interp_fwd(const float* base, const float* deltas, const float* labels, float* out, int B, int K, int D,
+                        void* stream);
+
+/* Latents -> displayable images tail of _latents_to_images (src/pipelines/inference/inference_pipeline_ip.py:483-485):
+ * y = clamp((clamp(x, -1, 1) + 1) / 2, 0, 1); x `dtype` (decoder output), y fp32. */
+int dadd_image_post_fwd(const void* x, float* y, int64_t n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DADD_B200_H */

@@ -1,0 +1,116 @@
+"""B200 implementation of DADD's baseline (no routing gates) cross-attention processor.
+
+Mirrors ``/root/reference/src/models/attention_processor_base.py``: ``OrdinalIPAttnProcessor2_0`` (:12-138),
+``get_frequency_mode_for_block`` (:141-167), ``set_ordinal_ip_attention_processors`` (:170-216).  One softmax over the
+concatenated [AOE | image] tokens; the reference's ``frequency_mode`` re-weighting multiplies the probabilities by a vector
+whose entries are all 1 (``scale_aoe = scale_ip = 1`` for every mode, :29-37) and renormalises, i.e. it is the identity up to
+one fp32 rounding (invariant I10) - so every mode runs the same single-segment launch of ``dadd_cross_attn_fwd``.
+"""
+
+from __future__ import annotations
+
+from typing import Literal, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, wcache
+from .attention_processor import COMPUTE_DTYPE, AttnProcessor2_0, _as_tokens, _finish, _reject_mask
+from .attention_processor_routing_gates import _hidden_size_of
+
+
+class OrdinalIPAttnProcessor2_0(nn.Module):
+    def __init__(
+        self,
+        hidden_size: int,
+        cross_attention_dim: Optional[int] = None,
+        num_image_tokens: int = 16,
+        num_aoe_tokens: int = 16,
+        frequency_mode: Literal["both", "aoe_dominant", "image_dominant"] = "both",
+    ) -> None:
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.cross_attention_dim = cross_attention_dim
+        self.num_image_tokens = num_image_tokens
+        self.num_aoe_tokens = num_aoe_tokens
+        self.frequency_mode = frequency_mode
+        self.scale_aoe = 1.0     # every mode of the reference sets both scales to 1 (:29-37)
+        self.scale_ip = 1.0
+
+    def project_kv(self, attn, encoder_hidden_states: torch.Tensor):
+        ehs = encoder_hidden_states
+        length = ehs.shape[1]
+        if length % 16 != 0 or length > 64:
+            raise NotImplementedError(f"dadd_cross_attn_fwd takes 16..64 condition tokens in multiples of 16, got {length}")
+
+        def build(w: torch.Tensor):
+            def fn():
+                p = F.linear(ehs.detach().to(w.dtype), w)
+                b, l, c = p.shape
+                return p.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(COMPUTE_DTYPE).contiguous()
+            return fn
+
+        src = (ehs, attn.to_k.weight, attn.to_v.weight)
+        tag = f"kv:{ehs.data_ptr()}:{tuple(ehs.shape)}"
+        return (wcache.get(self, "k" + tag, src, build(attn.to_k.weight)),
+                wcache.get(self, "v" + tag, src, build(attn.to_v.weight)), length)
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None, *args, **kwargs):
+        _reject_mask(attention_mask)
+        residual = hidden_states
+        out_dtype = hidden_states.dtype
+        x, shape4 = _as_tokens(attn, hidden_states, temb)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = x
+        elif getattr(attn, "norm_cross", None):
+            raise NotImplementedError(
+                "Cross-attention with separate encoder hidden states is not implemented in OrdinalIPAttnProcessor2_0.")
+        x = x.to(COMPUTE_DTYPE)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, COMPUTE_DTYPE))
+        k_cat, v_cat, length = self.project_kv(attn, encoder_hidden_states)
+        one = wcache.get(self, "one", (attn.to_q.weight,), lambda: torch.ones(1, device=x.device, dtype=torch.float32))
+        z = ops.cross_attention(q, k_cat, v_cat, one, attn.heads, length, 1)
+        return _finish(attn, z, residual, shape4, out_dtype)
+
+
+def get_frequency_mode_for_block(block_name: str) -> str:
+    """Reference :141-167 (low-resolution blocks AOE-dominant, high-resolution blocks image-dominant)."""
+    def index_after(token: str) -> Optional[int]:
+        try:
+            return int(block_name.split(token)[1].split(".")[0])
+        except (IndexError, ValueError):
+            return None
+
+    if "mid_block" in block_name:
+        return "aoe_dominant"
+    if "down_blocks" in block_name:
+        i = index_after("down_blocks.")
+        return "both" if i is None else ("image_dominant" if i <= 1 else "aoe_dominant")
+    if "up_blocks" in block_name:
+        i = index_after("up_blocks.")
+        return "both" if i is None else ("aoe_dominant" if i <= 1 else "image_dominant")
+    return "both"
+
+
+def set_ordinal_ip_attention_processors(unet, num_image_tokens: int = 16, num_aoe_tokens: int = 16,
+                                        use_frequency_strategy: bool = True) -> dict:
+    """Reference :170-216."""
+    procs: dict = {}
+    for name in unet.attn_processors.keys():
+        if name.endswith("attn1.processor"):
+            procs[name] = AttnProcessor2_0()
+            continue
+        mode = get_frequency_mode_for_block(name) if use_frequency_strategy else "both"
+        procs[name] = OrdinalIPAttnProcessor2_0(
+            hidden_size=_hidden_size_of(unet, name),
+            cross_attention_dim=unet.config.cross_attention_dim,
+            num_image_tokens=num_image_tokens,
+            num_aoe_tokens=num_aoe_tokens,
+            frequency_mode=mode,  # type: ignore[arg-type]
+        )
+    unet.set_attn_processor(procs)
+    return procs

@@ -1,0 +1,196 @@
+"""B200 implementation of DADD's triple-pathway cross-attention processor.
+
+Same class / function names, constructor arguments, buffers, state-dict keys and call protocol as
+``/root/reference/src/models/attention_processor_routing_gates.py`` (``SplitInjectionAttentionProcessor`` :12-196,
+``get_block_type`` :199-230, ``set_split_injection_processors`` :233-316), so it installs on a diffusers-style UNet through
+``unet.set_attn_processor`` and loads the reference's checkpoints.  What changes is the execution:
+
+* the three ``matmul / softmax / matmul`` pathways and the ``g_a z_a + g_d z_d + lambda z_delta`` merge (:148-178) are one
+  launch of ``dadd_cross_attn_fwd`` (segment softmaxes + gates fused, no score tensor in HBM);
+* the K/V projections of the condition tokens (:133-137,161-162) are step-invariant: they are computed once per distinct
+  ``encoder_hidden_states`` and cached as ``(B, H, 48, d)`` blocks in token order dis | anat | delta (I3);
+* ``delta_scale == 0`` skips the delta pathway entirely (I2), exactly like the reference's ``if self.delta_scale != 0.0``.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Literal, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, wcache
+from .attention_processor import COMPUTE_DTYPE, AttnProcessor2_0, _as_tokens, _finish, _reject_mask
+
+_ROLE_GATES: Dict[str, Tuple[float, float]] = {"anatomy": (0.5, 0.5), "disease": (0.5, 0.5), "both": (0.5, 0.5)}
+
+
+class SplitInjectionAttentionProcessor(nn.Module):
+    """Triple-pathway cross-attention (disease-AOE / anatomy-image / delta-AOE) with fixed per-block routing gates.
+
+    Constructor signature, attributes (``delta_scale`` is a plain mutable float that the sampler sets,
+    inference_pipeline_ip.py:311-318) and persistent buffers ``anat_gate`` / ``dis_gate`` follow the reference (:39-82).
+    """
+
+    def __init__(
+        self,
+        hidden_size: int,
+        cross_attention_dim: Optional[int] = None,
+        num_image_tokens: int = 16,
+        num_aoe_tokens: int = 16,
+        num_delta_tokens: int = 16,
+        block_type: Literal["anatomy", "disease", "both"] = "both",
+        anat_gate_init: Optional[float] = None,
+        dis_gate_init: Optional[float] = None,
+        delta_scale: float = 0.0,
+    ) -> None:
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.cross_attention_dim = cross_attention_dim
+        self.num_image_tokens = num_image_tokens
+        self.num_aoe_tokens = num_aoe_tokens
+        self.num_delta_tokens = num_delta_tokens
+        self.block_type = block_type
+        self.delta_scale = delta_scale
+        default_a, default_d = _ROLE_GATES[block_type]
+        self.register_buffer("anat_gate", torch.tensor(default_a if anat_gate_init is None else anat_gate_init))
+        self.register_buffer("dis_gate", torch.tensor(default_d if dis_gate_init is None else dis_gate_init))
+        kv_in = cross_attention_dim or hidden_size
+        self.to_k_dis = nn.Linear(kv_in, hidden_size, bias=False)
+        self.to_v_dis = nn.Linear(kv_in, hidden_size, bias=False)
+
+    # ------------------------------------------------------------------ step-invariant pieces
+    def _segments(self) -> int:
+        n = self.num_aoe_tokens
+        if not (self.num_image_tokens == n == self.num_delta_tokens and n % 16 == 0 and 3 * n <= 64):
+            raise NotImplementedError(
+                "dadd_cross_attn_fwd needs three equal token segments of 16 or a multiple of 16 tokens "
+                f"(got aoe={self.num_aoe_tokens}, image={self.num_image_tokens}, delta={self.num_delta_tokens})")
+        return n
+
+    def project_kv(self, attn, encoder_hidden_states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """K_cat / V_cat of shape (B, H, n_seg*16, d) in token order dis | anat | delta; cached per conditioning tensor."""
+        n = self._segments()
+        with_delta = self.delta_scale != 0.0
+        ehs = encoder_hidden_states
+        sources = (ehs, attn.to_k.weight, attn.to_v.weight, self.to_k_dis.weight, self.to_v_dis.weight)
+
+        def build(wa: torch.Tensor, wd: torch.Tensor):
+            def fn():
+                e = ehs.detach().to(wa.dtype)
+                dis, anat = e[:, :n, :], e[:, n:n + self.num_image_tokens, :]
+                parts = [F.linear(dis, wd), F.linear(anat, wa)]
+                if with_delta:
+                    parts.append(F.linear(e[:, -self.num_delta_tokens:, :], wd))
+                cat = torch.cat(parts, dim=1)                                   # (B, L, C)
+                b, l, c = cat.shape
+                return cat.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(COMPUTE_DTYPE).contiguous()
+            return fn
+
+        tag = f"kv{int(with_delta)}:{ehs.data_ptr()}:{tuple(ehs.shape)}"
+        k_cat = wcache.get(self, "k" + tag, sources, build(attn.to_k.weight, self.to_k_dis.weight))
+        v_cat = wcache.get(self, "v" + tag, sources, build(attn.to_v.weight, self.to_v_dis.weight))
+        return k_cat, v_cat, (3 if with_delta else 2)
+
+    def gate_vector(self) -> torch.Tensor:
+        """Device fp32[3] = (dis_gate, anat_gate, delta_scale): the per-segment weights in token order."""
+        lam = float(self.delta_scale)
+        stamp = (self.anat_gate.data_ptr(), self.anat_gate._version, self.dis_gate.data_ptr(), self.dis_gate._version, lam)
+        vec = self.__dict__.get("_gate_vec")
+        if vec is None or vec.device != self.anat_gate.device:
+            vec = torch.empty(3, device=self.anat_gate.device, dtype=torch.float32)
+            self.__dict__["_gate_vec"] = vec
+            self.__dict__["_gate_stamp"] = None
+        if self.__dict__["_gate_stamp"] != stamp:      # refreshed in place: the address is baked into captured graphs
+            with torch.no_grad():
+                vec[0].copy_(self.dis_gate.detach().float().reshape(()))
+                vec[1].copy_(self.anat_gate.detach().float().reshape(()))
+                vec[2].fill_(lam)
+            self.__dict__["_gate_stamp"] = stamp
+        return vec
+
+    # ------------------------------------------------------------------ diffusers processor protocol
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None, *args, **kwargs):
+        _reject_mask(attention_mask)
+        residual = hidden_states
+        out_dtype = hidden_states.dtype
+        x, shape4 = _as_tokens(attn, hidden_states, temb)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = x
+        x = x.to(COMPUTE_DTYPE)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, COMPUTE_DTYPE))
+        k_cat, v_cat, n_seg = self.project_kv(attn, encoder_hidden_states)
+        z = ops.cross_attention(q, k_cat, v_cat, self.gate_vector(), attn.heads, self.num_aoe_tokens, n_seg)
+        return _finish(attn, z, residual, shape4, out_dtype)
+
+
+def get_block_type(block_name: str) -> str:
+    """Role of a UNet block in the frequency routing: low-resolution blocks steer disease, high-resolution blocks
+    anatomy (reference :199-230; the 16-site table is SURVEY.md Appendix B.3)."""
+    def index_after(token: str) -> int:
+        return int(block_name.split(token)[1].split(".")[0])
+
+    if "mid_block" in block_name:
+        return "disease"
+    if "down_blocks" in block_name:
+        return "anatomy" if index_after("down_blocks.") < 2 else "disease"
+    if "up_blocks" in block_name:
+        return "anatomy" if index_after("up_blocks.") > 1 else "disease"
+    return "both"
+
+
+def _hidden_size_of(unet, name: str) -> int:
+    chans = list(unet.config.block_out_channels)
+    if name.startswith("mid_block"):
+        return chans[-1]
+    if name.startswith("up_blocks"):
+        return chans[::-1][int(name[len("up_blocks.")])]
+    if name.startswith("down_blocks"):
+        return chans[int(name[len("down_blocks.")])]
+    return chans[0]
+
+
+def set_split_injection_processors(
+    unet,
+    num_image_tokens: int = 16,
+    num_aoe_tokens: int = 16,
+    num_delta_tokens: int = 16,
+    use_frequency_strategy: bool = True,
+    delta_scale: float = 0.0,
+    gate_inits: Optional[Dict[str, Tuple[float, float]]] = None,
+) -> dict:
+    """Install the B200 processors on every attention site of ``unet`` (reference :233-316): ``attn1`` gets
+    ``AttnProcessor2_0`` (tcgen05 / mma.sync self-attention), ``attn2`` a ``SplitInjectionAttentionProcessor`` whose gates come
+    from ``gate_inits[role]`` = (anat_gate, dis_gate); afterwards the disease K/V are warm-started from the text K/V (I5)."""
+    gate_inits = dict(_ROLE_GATES) if gate_inits is None else gate_inits
+    procs: dict = {}
+    for name in unet.attn_processors.keys():
+        if name.endswith("attn1.processor"):
+            procs[name] = AttnProcessor2_0()
+            continue
+        role = get_block_type(name) if use_frequency_strategy else "both"
+        a_init, d_init = gate_inits.get(role, (0.5, 0.5))
+        procs[name] = SplitInjectionAttentionProcessor(
+            hidden_size=_hidden_size_of(unet, name),
+            cross_attention_dim=unet.config.cross_attention_dim,
+            num_image_tokens=num_image_tokens,
+            num_aoe_tokens=num_aoe_tokens,
+            num_delta_tokens=num_delta_tokens,
+            block_type=role,  # type: ignore[arg-type]
+            anat_gate_init=a_init,
+            dis_gate_init=d_init,
+            delta_scale=delta_scale,
+        )
+    unet.set_attn_processor(procs)
+    with torch.no_grad():
+        for module in unet.modules():
+            proc = getattr(module, "processor", None)
+            if isinstance(proc, SplitInjectionAttentionProcessor):
+                proc.to(device=module.to_k.weight.device)
+                proc.to_k_dis.weight.copy_(module.to_k.weight)
+                proc.to_v_dis.weight.copy_(module.to_v.weight)
+    return procs

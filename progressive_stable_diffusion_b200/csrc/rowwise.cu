@@ -1,0 +1,240 @@
+// Row-wise helpers of the transformer blocks and the Feature Purifier:
+//   LayerNorm (48 per UNet step + purifier), GEGLU gate, purifier multi-head attention core (16x16 per head),
+//   purifier gating epilogue (sigmoid gate * disease subtracted from the image tokens, fused with the final LayerNorm).
+// Reference: diffusers BasicTransformerBlock; src/models/feature_purifier.py:81-95.
+#include "common.cuh"
+
+namespace daddk {
+
+constexpr int LN_MAX_VEC = 8;  // 8 vectors x 8 elements x 32 lanes = C <= 2048
+
+// One warp per row, the row lives in registers: exact two-pass mean / variance in fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, T* __restrict__ y, int64_t rows,
+                                                        int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int nvec = C >> 3;
+    const T* xr = x + row * C;
+    T* yr = y + row * C;
+    float f[LN_MAX_VEC][8];
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j) {
+        const int iv = lane + j * 32;
+        if (iv < nvec) {
+            Vec8<T> t;
+            t.load(xr + (iv << 3));
+            t.unpack(f[j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum += f[j][i];
+        }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j) {
+        const int iv = lane + j * 32;
+        if (iv < nvec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; sq += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j) {
+        const int iv = lane + j * 32;
+        if (iv < nvec) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + (iv << 3));
+            const float4 g1 = *reinterpret_cast<const float4*>(gamma + (iv << 3) + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + (iv << 3));
+            const float4 b1 = *reinterpret_cast<const float4*>(beta + (iv << 3) + 4);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = (f[j][i] - mean) * rstd * g[i] + bb[i];
+            Vec8<T> t;
+            t.pack(o);
+            t.store(yr + (iv << 3));
+        }
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int inner) {
+    const int vec_per_row = inner >> 3;
+    const int64_t total = rows * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row;
+        const int j = (int)(i - r * vec_per_row) << 3;
+        Vec8<T> a, g;
+        a.load(x + r * 2 * inner + j);
+        g.load(x + r * 2 * inner + inner + j);
+        float fa[8], fg[8];
+        a.unpack(fa);
+        g.unpack(fg);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] *= gelu_erf(fg[k]);
+        a.pack(fa);
+        a.store(y + r * inner + j);
+    }
+}
+
+// nn.MultiheadAttention core for the purifier: one CTA per (sample, head); everything in shared memory.
+__global__ void __launch_bounds__(256) purifier_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                            const float* __restrict__ v, float* __restrict__ o, int Lq,
+                                                            int Lk, int D, int heads) {
+    extern __shared__ float sm[];
+    const int hd = D / heads;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    float* sq = sm;                 // [Lq][hd+1]
+    float* sk = sq + Lq * (hd + 1); // [Lk][hd+1]
+    float* sv = sk + Lk * (hd + 1); // [Lk][hd+1]
+    float* sp = sv + Lk * (hd + 1); // [Lq][Lk]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Lq * hd; i += blockDim.x) {
+        const int r = i / hd, c = i % hd;
+        sq[r * (hd + 1) + c] = q[((int64_t)b * Lq + r) * D + h * hd + c];
+    }
+    for (int i = tid; i < Lk * hd; i += blockDim.x) {
+        const int r = i / hd, c = i % hd;
+        sk[r * (hd + 1) + c] = k[((int64_t)b * Lk + r) * D + h * hd + c];
+        sv[r * (hd + 1) + c] = v[((int64_t)b * Lk + r) * D + h * hd + c];
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)hd);
+    for (int i = tid; i < Lq * Lk; i += blockDim.x) {
+        const int r = i / Lk, c = i % Lk;
+        float acc = 0.0f;
+        for (int e = 0; e < hd; ++e) acc = fmaf(sq[r * (hd + 1) + e], sk[c * (hd + 1) + e], acc);
+        sp[i] = acc * scale;
+    }
+    __syncthreads();
+    if (tid < Lq) {
+        float m = -INFINITY;
+        for (int c = 0; c < Lk; ++c) m = fmaxf(m, sp[tid * Lk + c]);
+        float s = 0.0f;
+        for (int c = 0; c < Lk; ++c) { const float e = expf(sp[tid * Lk + c] - m); sp[tid * Lk + c] = e; s += e; }
+        const float inv = 1.0f / s;
+        for (int c = 0; c < Lk; ++c) sp[tid * Lk + c] *= inv;
+    }
+    __syncthreads();
+    for (int i = tid; i < Lq * hd; i += blockDim.x) {
+        const int r = i / hd, c = i % hd;
+        float acc = 0.0f;
+        for (int j = 0; j < Lk; ++j) acc = fmaf(sp[r * Lk + j], sv[j * (hd + 1) + c], acc);
+        o[((int64_t)b * Lq + r) * D + h * hd + c] = acc;
+    }
+}
+
+// e_clean = img - sigmoid(logit) * disease ; y = LayerNorm(e_clean).  One warp per row, D <= 2048.
+__global__ void __launch_bounds__(256) purifier_gate_ln_kernel(const float* __restrict__ img,
+                                                               const float* __restrict__ logits,
+                                                               const float* __restrict__ disease,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ y,
+                                                               int64_t rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int per = (D + 31) / 32;      // <= 64
+    float f[64];
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int c = lane + j * 32;
+        if (j < per && c < D) {
+            const int64_t i = row * D + c;
+            const float gate = 1.0f / (1.0f + expf(-logits[i]));
+            f[j] = img[i] - gate * disease[i];
+            sum += f[j];
+        }
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int c = lane + j * 32;
+        if (j < per && c < D) { const float d = f[j] - mean; sq += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int c = lane + j * 32;
+        if (j < per && c < D) y[row * D + c] = (f[j] - mean) * rstd * gamma[c] + beta[c];
+    }
+}
+
+}  // namespace daddk
+
+using namespace daddk;
+
+extern "C" {
+
+int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps,
+                       int dtype, void* stream) {
+    DADD_REQUIRE(x && y && gamma && beta && rows >= 0, "dadd_layernorm_fwd");
+    DADD_REQUIRE(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 256, "dadd_layernorm_fwd");
+    DADD_REQUIRE(dtype == DADD_F32 || dtype == DADD_BF16, "dadd_layernorm_fwd");
+    if (rows == 0) return 0;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    if (dtype == DADD_BF16)
+        layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, rows, C, eps);
+    else
+        layernorm_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta, (float*)y,
+                                                                             rows, C, eps);
+    return launched("dadd_layernorm_fwd");
+}
+
+int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream) {
+    DADD_REQUIRE(x && y && rows >= 0 && inner > 0 && inner % 8 == 0, "dadd_geglu_fwd");
+    DADD_REQUIRE(dtype == DADD_F32 || dtype == DADD_BF16, "dadd_geglu_fwd");
+    if (rows == 0) return 0;
+    const int64_t total = rows * (inner / 8);
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (dtype == DADD_BF16)
+        geglu_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
+                                                                                   (__nv_bfloat16*)y, rows, inner);
+    else
+        geglu_kernel<float><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, rows, inner);
+    return launched("dadd_geglu_fwd");
+}
+
+int dadd_purifier_attn_fwd(const float* q, const float* k, const float* v, float* o, int B, int Lq, int Lk, int D,
+                           int heads, void* stream) {
+    DADD_REQUIRE(q && k && v && o, "dadd_purifier_attn_fwd");
+    DADD_REQUIRE(B >= 0 && Lq > 0 && Lk > 0 && Lq <= 32 && Lk <= 32, "dadd_purifier_attn_fwd");
+    DADD_REQUIRE(heads > 0 && D % heads == 0 && D / heads <= 128, "dadd_purifier_attn_fwd");
+    if (B == 0) return 0;
+    const int hd = D / heads;
+    const size_t smem = ((size_t)(Lq + 2 * Lk) * (hd + 1) + (size_t)Lq * Lk) * sizeof(float);
+    if (smem > 48 * 1024) {
+        if (cuda_ok(cudaFuncSetAttribute(purifier_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "dadd_purifier_attn_fwd"))
+            return 2;
+    }
+    purifier_attn_kernel<<<B * heads, 256, smem, (cudaStream_t)stream>>>(q, k, v, o, Lq, Lk, D, heads);
+    return launched("dadd_purifier_attn_fwd");
+}
+
+int dadd_purifier_gate_ln_fwd(const float* img, const float* gate_logits, const float* disease, const float* gamma,
+                              const float* beta, float* y, int64_t rows, int D, float eps, void* stream) {
+    DADD_REQUIRE(img && gate_logits && disease && gamma && beta && y, "dadd_purifier_gate_ln_fwd");
+    DADD_REQUIRE(rows >= 0 && D > 0 && D <= 2048, "dadd_purifier_gate_ln_fwd");
+    if (rows == 0) return 0;
+    const int wpb = 8;
+    purifier_gate_ln_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        img, gate_logits, disease, gamma, beta, y, rows, D, eps);
+    return launched("dadd_purifier_gate_ln_fwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Tensor-level wrappers over the C ABI (``include/dadd_b200.h``).
+
+PyTorch is used for device memory and streams only: every function below hands raw ``data_ptr()``s and the current
+CUDA stream to ``libdadd_b200.so``.  All of them are CUDA-graph capturable (nothing synchronises) and none has a CPU or
+eager fallback: CPU tensors raise.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+NCHW, NHWC = 0, 1
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"dadd kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.DaddError("dadd kernels run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------------- DDIM
+def ddim_step_(x: torch.Tensor, eps_cond: torch.Tensor, eps_uncond: Optional[torch.Tensor], guidance: float,
+               sqrt_ab_t: float, sqrt_1mab_t: float, sqrt_ab_prev: float, eps_coef: float, sigma: float = 0.0,
+               noise: Optional[torch.Tensor] = None, clamp: float = 4.0, is_last: bool = False) -> torch.Tensor:
+    """In-place fused CFG + x0 + clamp + DDIM update (inference_pipeline_ip.py:427-468)."""
+    _cuda(x, eps_cond, eps_uncond, noise)
+    assert x.dtype == torch.float32 and x.is_contiguous() and eps_cond.is_contiguous()
+    assert eps_cond.numel() == x.numel() and (eps_uncond is None or (eps_uncond.is_contiguous() and eps_uncond.dtype == eps_cond.dtype))
+    assert noise is None or (noise.dtype == torch.float32 and noise.is_contiguous() and noise.numel() == x.numel())
+    _lib.check(_lib.load().dadd_ddim_step(x.data_ptr(), eps_cond.data_ptr(), _ptr(eps_uncond), _dt(eps_cond), guidance,
+                                          sqrt_ab_t, sqrt_1mab_t, sqrt_ab_prev, eps_coef, sigma, _ptr(noise), clamp,
+                                          int(is_last), x.numel(), _stream()), "dadd_ddim_step")
+    return x
+
+
+def ddim_step_table_(x: torch.Tensor, eps_cond: torch.Tensor, eps_uncond: Optional[torch.Tensor], guidance: float,
+                     coef_table: torch.Tensor, step_state: torch.Tensor, noise: Optional[torch.Tensor] = None,
+                     clamp: float = 4.0) -> torch.Tensor:
+    _cuda(x, eps_cond, eps_uncond, coef_table, step_state, noise)
+    assert x.dtype == torch.float32 and x.is_contiguous() and eps_cond.is_contiguous()
+    assert coef_table.dtype == torch.float32 and coef_table.shape[-1] == 8 and coef_table.is_contiguous()
+    assert step_state.dtype == torch.int32 and step_state.numel() == 2
+    _lib.check(_lib.load().dadd_ddim_step_table(x.data_ptr(), eps_cond.data_ptr(), _ptr(eps_uncond), _dt(eps_cond),
+                                                guidance, coef_table.data_ptr(), step_state.data_ptr(), _ptr(noise),
+                                                clamp, x.numel(), _stream()), "dadd_ddim_step_table")
+    return x
+
+
+def step_begin_(step_state: torch.Tensor, table: Optional[torch.Tensor] = None, row_out: Optional[torch.Tensor] = None) -> None:
+    _cuda(step_state, table, row_out)
+    row_bytes = 0
+    if table is not None:
+        assert table.is_contiguous() and row_out.is_contiguous() and table.dtype == row_out.dtype
+        row_bytes = row_out.numel() * row_out.element_size()
+        assert table[0].numel() == row_out.numel()
+    _lib.check(_lib.load().dadd_step_begin(step_state.data_ptr(), _ptr(table), _ptr(row_out), row_bytes, _stream()),
+               "dadd_step_begin")
+
+
+# --------------------------------------------------------------------------------------------- norms
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, num_groups: int, eps: float, silu: bool,
+               chan_add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) of a 4-D ``(B, C, H, W)`` tensor, either contiguous (NCHW) or channels_last (NHWC) in memory.
+    ``chan_add`` (B, C) fp32 is added to x before the statistics (the resnet time-embedding term)."""
+    _cuda(x, gamma, beta, chan_add)
+    assert x.dim() == 4
+    b, c, h, w = x.shape
+    if x.is_contiguous():            # (when C == 1 or H*W == 1 both layouts describe the same bytes)
+        layout = NCHW
+    elif x.is_contiguous(memory_format=torch.channels_last):
+        layout = NHWC
+    else:
+        raise ValueError("group_norm needs a contiguous or channels_last tensor")
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    if chan_add is not None:
+        assert chan_add.dtype == torch.float32 and chan_add.shape == (b, c) and chan_add.stride(1) == 1
+    y = torch.empty_like(x) if out is None else out
+    assert y.stride() == x.stride()
+    _lib.check(_lib.load().dadd_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(chan_add),
+                                              0 if chan_add is None else chan_add.stride(0), y.data_ptr(), b, c, h * w, num_groups, eps, int(silu), layout, _dt(x),
+                                              _stream()), "dadd_groupnorm_fwd")
+    return y
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _cuda(x, gamma, beta)
+    assert x.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    c = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().dadd_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                              x.numel() // c, c, eps, _dt(x), _stream()), "dadd_layernorm_fwd")
+    return y
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    """``a * gelu(gate)`` with ``[a | gate] = x.chunk(2, -1)`` (diffusers GEGLU)."""
+    _cuda(x)
+    assert x.is_contiguous() and x.shape[-1] % 16 == 0
+    inner = x.shape[-1] // 2
+    y = torch.empty(*x.shape[:-1], inner, device=x.device, dtype=x.dtype)
+    _lib.check(_lib.load().dadd_geglu_fwd(x.data_ptr(), y.data_ptr(), x.numel() // x.shape[-1], inner, _dt(x), _stream()),
+               "dadd_geglu_fwd")
+    return y
+
+
+# --------------------------------------------------------------------------------------------- attention
+def _rows(t: torch.Tensor) -> int:
+    """Row stride (elements) of a (B, N, *) view whose last dim is dense and whose batch stride is N * row stride."""
+    assert t.dim() == 3 and t.stride(2) == 1, "attention operands must be (B, N, C) with unit inner stride"
+    assert t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1), "batch stride must equal N * row stride"
+    return t.stride(1)
+
+
+def cross_attention(q: torch.Tensor, k_cat: torch.Tensor, v_cat: torch.Tensor, gates: torch.Tensor, heads: int,
+                    seg_len: int, n_seg: int, scale: Optional[float] = None) -> torch.Tensor:
+    """sum_s gates[s] softmax(q k_s^T scale) v_s; q (B,N,H*d) bf16 (may be a strided view), k_cat/v_cat (B,H,L,d)."""
+    _cuda(q, k_cat, v_cat, gates)
+    b, n, c = q.shape
+    d = c // heads
+    assert q.dtype == torch.bfloat16 and k_cat.dtype == torch.bfloat16 and v_cat.dtype == torch.bfloat16
+    assert k_cat.is_contiguous() and v_cat.is_contiguous() and k_cat.shape == (b, heads, seg_len * n_seg, d) == v_cat.shape
+    assert gates.dtype == torch.float32 and gates.numel() >= n_seg
+    o = torch.empty(b, n, c, device=q.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().dadd_cross_attn_fwd(q.data_ptr(), _rows(q), k_cat.data_ptr(), v_cat.data_ptr(), o.data_ptr(), c,
+                                               b, heads, n, d, seg_len, n_seg, gates.data_ptr(),
+                                               float(d ** -0.5 if scale is None else scale), _stream()),
+               "dadd_cross_attn_fwd")
+    return o
+
+
+def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None) -> torch.Tensor:
+    """softmax(q k^T scale) v per head; q,k,v (B,N,H*d) bf16, possibly strided views of one fused QKV buffer."""
+    _cuda(q, k, v)
+    b, n, c = q.shape
+    d = c // heads
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16 and k.shape == q.shape == v.shape
+    o = torch.empty(b, n, c, device=q.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().dadd_self_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _rows(q), _rows(k), _rows(v),
+                                              o.data_ptr(), c, b, heads, n, d,
+                                              float(d ** -0.5 if scale is None else scale), _stream()),
+               "dadd_self_attn_fwd")
+    return o
+
+
+# --------------------------------------------------------------------------------------------- conditioning front end
+def purifier_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    _cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.float32 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    b, lq, dm = q.shape
+    o = torch.empty_like(q)
+    _lib.check(_lib.load().dadd_purifier_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), b, lq, k.shape[1],
+                                                  dm, heads, _stream()), "dadd_purifier_attn_fwd")
+    return o
+
+
+def purifier_gate_ln(img: torch.Tensor, gate_logits: torch.Tensor, disease: torch.Tensor, gamma: torch.Tensor,
+                     beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _cuda(img, gate_logits, disease, gamma, beta)
+    for t in (img, gate_logits, disease, gamma, beta):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    dm = img.shape[-1]
+    y = torch.empty_like(img)
+    _lib.check(_lib.load().dadd_purifier_gate_ln_fwd(img.data_ptr(), gate_logits.data_ptr(), disease.data_ptr(),
+                                                     gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), img.numel() // dm, dm,
+                                                     eps, _stream()), "dadd_purifier_gate_ln_fwd")
+    return y
+
+
+def aoe_interp(base: torch.Tensor, deltas: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    _cuda(base, deltas, labels)
+    for t in (base, deltas, labels):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    k, dm = deltas.shape[0] + 1, base.shape[0]
+    out = torch.empty(labels.shape[0], dm, device=base.device, dtype=torch.float32)
+    _lib.check(_lib.load().dadd_aoe_interp_fwd(base.data_ptr(), deltas.data_ptr(), labels.data_ptr(), out.data_ptr(),
+                                               labels.shape[0], k, dm, _stream()), "dadd_aoe_interp_fwd")
+    return out
+
+
+def image_post(x: torch.Tensor) -> torch.Tensor:
+    """clamp(-1,1) -> (x+1)/2 -> clamp(0,1) (inference_pipeline_ip.py:483-485); returns fp32 with x's strides."""
+    _cuda(x)
+    y = torch.empty_like(x, dtype=torch.float32)
+    assert y.stride() == x.stride()
+    _lib.check(_lib.load().dadd_image_post_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _dt(x), _stream()), "dadd_image_post_fwd")
+    return y

@@ -1,0 +1,66 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/dadd_b200.h declares (no compute calls)."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dadd_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dadd_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__.build()
+    from progressive_stable_diffusion_b200 import _lib
+    return _lib
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for n in ("dadd_ddim_step", "dadd_ddim_step_table", "dadd_step_begin", "dadd_groupnorm_fwd", "dadd_layernorm_fwd",
+              "dadd_geglu_fwd", "dadd_cross_attn_fwd", "dadd_self_attn_fwd", "dadd_purifier_attn_fwd",
+              "dadd_purifier_gate_ln_fwd", "dadd_aoe_interp_fwd", "dadd_image_post_fwd", "dadd_last_error",
+              "dadd_abi_version", "dadd_launch_count", "dadd_reset_launch_count"):
+        assert n in names, n
+
+
+def test_library_exports_every_declared_symbol(lib):
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    for n in _declared():
+        assert hasattr(cdll, n), f"{n} declared in dadd_b200.h but not exported by libdadd_b200.so"
+
+
+def test_ctypes_table_covers_the_header(lib):
+    helpers = {"dadd_last_error", "dadd_abi_version", "dadd_launch_count", "dadd_reset_launch_count"}
+    assert set(lib.SIGNATURES) == set(_declared()) - helpers
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, args in lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", src, flags=re.S)
+        assert m, name
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(args), name
+
+
+def test_abi_version_and_error_channel(lib):
+    l = lib.load()
+    assert l.dadd_abi_version() == 1
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    rc = l.dadd_groupnorm_fwd(None, None, None, None, 0, None, 1, 320, 64, 32, 1e-5, 1, 1, 1, None)
+    assert rc != 0 and b"dadd_groupnorm_fwd" in l.dadd_last_error()
+    rc = l.dadd_cross_attn_fwd(1, 320, 1, 1, 1, 320, 1, 8, 64, 41, 16, 3, 1, 0.1, None)
+    assert rc != 0 and b"d % 8" in l.dadd_last_error()
+
+
+def test_missing_library_fails_loudly(lib, monkeypatch):
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libdadd_b200.so")
+    with pytest.raises(lib.DaddError):
+        lib.load()

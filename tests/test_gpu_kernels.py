@@ -1,0 +1,260 @@
+"""Parity of each sm_100a kernel (called through the C ABI wrappers) against the CPU oracle / golden vectors."""
+
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import conditioning, processors, sampler  # noqa: E402
+from tests.golden import cases  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_modules.npz"))
+DEV = "cuda:0"
+
+
+def _ops():
+    from progressive_stable_diffusion_b200 import ops
+    return ops
+
+
+def rel_err(a: torch.Tensor, ref: torch.Tensor) -> float:
+    """max |a - ref| / max |ref| : the 'max relative error' of BASELINE.md section 4."""
+    return ((a.double().cpu() - ref.double().cpu()).abs().max() / ref.double().abs().max().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ DDIM (bit-exact)
+@pytest.mark.parametrize("eta", [0.0, 0.5])
+@pytest.mark.parametrize("cfg", [False, True])
+@pytest.mark.parametrize("eps_dtype", [torch.float32, torch.bfloat16])
+def test_ddim_step_bit_exact_all_schedule_positions(eta, cfg, eps_dtype):
+    ops = _ops()
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import ddim_schedule
+    _, ac = sampler.build_noise_schedule()
+    ts, table = ddim_schedule(ac, 1000, 50, eta)
+    assert ts.tolist() == sampler.ddim_timesteps().tolist()
+    g = torch.Generator().manual_seed(5)
+    n = 13 * 4 * 32 * 32
+    x = torch.randn(n, generator=g) * 3
+    for i in range(50):
+        ec = torch.randn(n, generator=g).to(eps_dtype)
+        eu = torch.randn(n, generator=g).to(eps_dtype) if cfg else None
+        noise = torch.randn(n, generator=g)
+        eps_ref = sampler.cfg_combine(ec.float(), eu.float(), 2.5) if cfg else ec.float()
+        t_prev = None if i == 49 else int(ts[i + 1])
+        want = sampler.ddim_update(x, eps_ref, ac, int(ts[i]), t_prev, eta, noise)
+        row = table[i].tolist()
+        got = ops.ddim_step_(x.to(DEV).clone(), ec.to(DEV), None if eu is None else eu.to(DEV), 2.5, row[0], row[1], row[2],
+                             row[3], row[4], noise.to(DEV) if eta else None, 4.0, bool(row[5]))
+        assert torch.equal(got.cpu(), want), f"step {i}: max diff {(got.cpu() - want).abs().max()}"
+        x = want if i < 49 else x
+
+
+def test_ddim_step_table_matches_scalar_version():
+    ops = _ops()
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import ddim_schedule
+    _, ac = sampler.build_noise_schedule()
+    ts, table = ddim_schedule(ac, 1000, 50, 0.0)
+    g = torch.Generator().manual_seed(6)
+    n = 4096 * 3 + 5
+    x0 = torch.randn(n, generator=g)
+    eps = torch.randn(50, n, generator=g)
+    terms = torch.randn(50, 64, generator=g)
+    xa = x0.to(DEV).clone()
+    xb = x0.to(DEV).clone()
+    state = torch.zeros(2, dtype=torch.int32, device=DEV)
+    row_out = torch.zeros(1, 64, device=DEV)
+    tab = table.to(DEV)
+    for i in range(50):
+        r = table[i].tolist()
+        ops.ddim_step_(xa, eps[i].to(DEV), None, 1.0, r[0], r[1], r[2], r[3], r[4], None, 4.0, bool(r[5]))
+        ops.step_begin_(state, terms.to(DEV), row_out)
+        assert torch.equal(row_out.cpu()[0], terms[i])
+        ops.ddim_step_table_(xb, eps[i].to(DEV), None, 1.0, tab, state, None, 4.0)
+        assert torch.equal(xa, xb)
+    assert state.tolist() == [49, 50]
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+GN_SHAPES = [(320, 32), (640, 32), (960, 32), (320, 16), (640, 16), (1280, 16), (1920, 16), (640, 8), (1280, 8), (1920, 8),
+             (2560, 8), (1280, 4), (2560, 4), (128, 64), (512, 32)]
+
+
+@pytest.mark.parametrize("c,hw", GN_SHAPES)
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
+def test_groupnorm_silu_bf16(c, hw, layout):
+    ops = _ops()
+    g = torch.Generator().manual_seed(c + hw)
+    b = 3
+    x = (torch.randn(b, c, hw, hw, generator=g) * 1.5 + 0.7).to(torch.bfloat16)
+    gamma = 1 + 0.2 * torch.randn(c, generator=g)
+    beta = 0.2 * torch.randn(c, generator=g)
+    add = torch.randn(b, c, generator=g)
+    for silu, use_add, eps in ((True, False, 1e-5), (True, True, 1e-5), (False, False, 1e-6)):
+        xin = x.float() + (add[:, :, None, None] if use_add else 0)
+        ref = F.group_norm(xin, 32, gamma, beta, eps)
+        ref = F.silu(ref) if silu else ref
+        xd = x.to(DEV)
+        if layout == "nhwc":
+            xd = xd.contiguous(memory_format=torch.channels_last)
+        y = ops.group_norm(xd, gamma.to(DEV), beta.to(DEV), 32, eps, silu, add.to(DEV) if use_add else None)
+        assert y.stride() == xd.stride()
+        err = (y.float().cpu() - ref).abs().max().item()
+        assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), (c, hw, layout, silu, use_add, err)
+
+
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
+def test_groupnorm_fp32_and_large_mean(layout):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 320, 16, 16, generator=g) * 0.1 + 30.0          # |mean| >> std: cancellation trap
+    gamma, beta = torch.ones(320), torch.zeros(320)
+    ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5).float()
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last) if layout == "nhwc" else x.to(DEV)
+    y = ops.group_norm(xd, gamma.to(DEV), beta.to(DEV), 32, 1e-5, False)
+    assert (y.cpu() - ref).abs().max().item() < 2e-3
+
+
+def test_groupnorm_expanded_chan_add_row():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4, 320, 8, 8, generator=g).to(torch.bfloat16)
+    row = torch.randn(1, 640, generator=g)
+    gamma, beta = torch.ones(320), torch.zeros(320)
+    add = row[:, 320:].expand(4, -1)                                     # stride-0 rows, offset view
+    ref = F.silu(F.group_norm(x.float() + add[:, :, None, None], 32, gamma, beta, 1e-5))
+    y = ops.group_norm(x.to(DEV).contiguous(memory_format=torch.channels_last), gamma.to(DEV), beta.to(DEV), 32, 1e-5, True,
+                       row.to(DEV)[:, 320:].expand(4, -1))
+    assert (y.float().cpu() - ref).abs().max().item() < 0.04
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm / GEGLU
+@pytest.mark.parametrize("c", [320, 640, 1280, 768])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_layernorm(c, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(c)
+    x = (torch.randn(3, 77, c, generator=g) * 2 + 0.5).to(dtype)
+    gamma, beta = 1 + 0.1 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    y = ops.layer_norm(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5)
+    tol = 2.0 ** -7 * ref.abs().max().item() if dtype == torch.bfloat16 else 2e-5
+    assert (y.float().cpu() - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("inner", [1280, 2560, 5120])
+def test_geglu(inner):
+    ops = _ops()
+    g = torch.Generator().manual_seed(inner)
+    x = (torch.randn(2, 50, 2 * inner, generator=g) * 2).to(torch.bfloat16)
+    a, gate = x.float().chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    y = ops.geglu(x.to(DEV))
+    assert (y.float().cpu() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ attention cores
+@pytest.mark.parametrize("n,d,b", [(1024, 40, 2), (256, 80, 2), (64, 160, 3), (16, 160, 2), (100, 40, 1), (4096, 40, 1),
+                                   (200, 64, 1), (130, 128, 1)])
+def test_self_attention_core(n, d, b):
+    ops = _ops()
+    h = 8
+    g = torch.Generator().manual_seed(n + d)
+    qkv = (torch.randn(b, n, 3 * h * d, generator=g) * 1.2).to(torch.bfloat16)
+    c = h * d
+    q, k, v = (qkv[..., i * c:(i + 1) * c].float().view(b, n, h, d).transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+    qd = qkv.to(DEV)
+    o = ops.self_attention(qd[..., :c], qd[..., c:2 * c], qd[..., 2 * c:], h)
+    assert rel_err(o, ref) <= 1.5e-2, rel_err(o, ref)
+
+
+@pytest.mark.parametrize("case", cases.PROCESSOR_CASES, ids=lambda c: c["name"])
+def test_cross_attention_processors_vs_reference_golden(case):
+    """Product processor (fused kernel, bf16) vs the VERBATIM reference processor's fp32 output."""
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200.unet2d import Attention
+    w, x, ehs = cases.processor_inputs(case)
+    c = case["c"]
+    attn = Attention(c, 768, 8, c // 8)
+    if case["kind"] == "split":
+        proc = P.SplitInjectionAttentionProcessor(c, 768, 16, 16, 16, "both", case["gates"][0], case["gates"][1],
+                                                  case["delta_scale"])
+    else:
+        proc = P.OrdinalIPAttnProcessor2_0(c, 768, 16, 16, case["mode"])
+    attn.set_processor(proc)
+    attn.load_state_dict(w)
+    attn.to(DEV)
+    with torch.no_grad():
+        out = attn(x.to(DEV), encoder_hidden_states=ehs.to(DEV))
+    assert out.dtype == torch.float32
+    ref = torch.from_numpy(GOLD["processor_" + case["name"]])
+    assert rel_err(out, ref) <= 2e-2, rel_err(out, ref)
+
+
+def test_cross_attention_delta_zero_skips_pathway():
+    """I2: delta_scale == 0 must equal a 2-segment launch regardless of what the delta tokens hold (even NaN)."""
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200.unet2d import Attention
+    case = cases.PROCESSOR_CASES[1]
+    w, x, ehs = cases.processor_inputs(case)
+    attn = Attention(320, 768, 8, 40)
+    proc = P.SplitInjectionAttentionProcessor(320, 768, delta_scale=0.0, anat_gate_init=0.1, dis_gate_init=0.9)
+    attn.set_processor(proc)
+    attn.load_state_dict(w)
+    attn.to(DEV)
+    ehs_nan = ehs.clone()
+    ehs_nan[:, -16:] = float("nan")
+    with torch.no_grad():
+        a = attn(x.to(DEV), encoder_hidden_states=ehs.to(DEV))
+        b = attn(x.to(DEV), encoder_hidden_states=ehs_nan.to(DEV))
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ conditioning front end
+def test_purifier_matches_reference_golden():
+    import progressive_stable_diffusion_b200 as P
+    w, img, aoe = cases.purifier_inputs()
+    pur = P.FeaturePurifier(768, 8, 2)
+    pur.load_state_dict(w)
+    pur.to(DEV)
+    with torch.no_grad():
+        out = pur(img.to(DEV), aoe.to(DEV))
+    torch.testing.assert_close(out.cpu(), torch.from_numpy(GOLD["purifier"]), atol=2e-4, rtol=1e-4)
+
+
+def test_aoe_matches_reference_golden():
+    import progressive_stable_diffusion_b200 as P
+    w, labels, src = cases.aoe_inputs()
+    emb = P.AdditiveOrdinalEmbedder(4, 768, delta_scale=0.05, num_tokens=16)
+    emb.load_state_dict(w)
+    emb.to(DEV)
+    with torch.no_grad():
+        torch.testing.assert_close(emb(labels.to(DEV)).cpu(), torch.from_numpy(GOLD["aoe_forward"]), atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(emb.get_negative_embedding(labels.to(DEV)).cpu(), torch.from_numpy(GOLD["aoe_negative"]),
+                                   atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(emb.get_ordinal_delta_embedding(src.to(DEV), labels.to(DEV)).cpu(),
+                                   torch.from_numpy(GOLD["aoe_delta"]), atol=4e-5, rtol=1e-4)
+        same = emb.get_ordinal_delta_embedding(labels.to(DEV), labels.to(DEV))
+        assert same.abs().max().item() == 0.0                                           # invariant I1
+        # interpolation itself: table + gather + lerp, vs the oracle restatement
+        interp = emb._interp(labels.to(DEV)).cpu()
+        torch.testing.assert_close(interp, conditioning.aoe_interp(w, labels), atol=1e-7, rtol=1e-6)
+
+
+def test_image_post():
+    ops = _ops()
+    x = torch.linspace(-2, 2, 1001)
+    ref = ((x.clamp(-1, 1) + 1) / 2).clamp(0, 1)
+    assert torch.equal(ops.image_post(x.to(DEV)).cpu(), ref)
+
+
+def test_cpu_tensors_are_rejected():
+    ops = _ops()
+    from progressive_stable_diffusion_b200._lib import DaddError
+    with pytest.raises(DaddError):
+        ops.layer_norm(torch.zeros(2, 320), torch.ones(320), torch.zeros(320))

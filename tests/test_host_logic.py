@@ -1,0 +1,127 @@
+"""CPU tests of the host-side mirror of the reference interface: names, role maps, token layout, schedule tables,
+state-dict keys, error behaviour.  (Invariants I3-I9 of SURVEY.md section 4.)"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import progressive_stable_diffusion_b200 as P
+from oracle import sampler, weights
+from oracle import processors as oproc
+from progressive_stable_diffusion_b200 import parallel
+from progressive_stable_diffusion_b200.inference_pipeline_ip import _build_labels, ddim_schedule
+from tests.golden import cases
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_modules.npz"))
+
+B1_TIMESTEPS = [999, 978, 958, 937, 917, 897, 876, 856, 835, 815, 795, 774, 754, 733, 713, 693, 672, 652, 632, 611, 591, 570,
+                550, 530, 509, 489, 468, 448, 428, 407, 387, 366, 346, 326, 305, 285, 265, 244, 224, 203, 183, 163, 142, 122,
+                101, 81, 61, 40, 20, 0]
+
+
+@pytest.fixture(scope="module")
+def module():
+    return P.DiffusionModuleWithIP(P.default_config(), build_vae=False)
+
+
+def test_role_and_frequency_maps_bit_exact_vs_reference():
+    names = cases.cross_attention_processor_names()
+    assert [P.get_block_type(n) for n in names] == list(GOLD["roles"])
+    assert [P.get_frequency_mode_for_block(n) for n in names] == list(GOLD["freq_modes"])
+    assert P.get_block_type("conv_in") == "both" and P.get_frequency_mode_for_block("down_blocks.x") == "both"
+
+
+def test_processor_installation(module):
+    unet = module.unet.unet
+    procs = unet.attn_processors
+    assert len(procs) == 32
+    names = list(procs)
+    assert names[0] == "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor"
+    for name, proc in procs.items():
+        if name.endswith("attn1.processor"):
+            assert isinstance(proc, P.AttnProcessor2_0)
+            continue
+        assert isinstance(proc, P.SplitInjectionAttentionProcessor)
+        role = P.get_block_type(name)
+        want = {"anatomy": (0.1, 0.9), "disease": (0.9, 0.1)}[role]
+        assert proc.block_type == role
+        assert (round(proc.anat_gate.item(), 6), round(proc.dis_gate.item(), 6)) == want
+        assert (proc.num_aoe_tokens, proc.num_image_tokens, proc.num_delta_tokens) == (16, 16, 16)
+    # I5: disease K/V warm-started from the text K/V
+    for mod in unet.modules():
+        proc = getattr(mod, "processor", None)
+        if isinstance(proc, P.SplitInjectionAttentionProcessor):
+            assert torch.equal(proc.to_k_dis.weight, mod.to_k.weight) and torch.equal(proc.to_v_dis.weight, mod.to_v.weight)
+    with pytest.raises(ValueError):
+        unet.set_attn_processor({"x": P.AttnProcessor2_0()})
+
+
+def test_state_dict_keys_equal_lightning_checkpoint_layout():
+    m = P.DiffusionModuleWithIP(P.default_config())
+    ref = weights.make_module_state(0)
+    sd = m.state_dict()
+    assert set(sd) == set(ref)
+    assert all(sd[k].shape == ref[k].shape for k in sd)
+    assert "alphas_cumprod" not in sd                                     # schedule buffers are non-persistent
+    assert "unet.unet.mid_block.attentions.0.transformer_blocks.0.attn2.processor.anat_gate" in sd   # gates persistent
+
+
+def test_schedule_and_labels(module):
+    _, ac = sampler.build_noise_schedule()
+    assert torch.equal(module.alphas_cumprod, ac)
+    assert abs(ac[0].item() - 0.99915) < 1e-6 and abs(ac[999].item() - 0.0015790) < 1e-6 and abs(ac[978].item() - 0.0020298) < 1e-6
+    ts, table = ddim_schedule(ac, 1000, 50, 0.0)
+    assert ts.tolist() == B1_TIMESTEPS == sampler.ddim_timesteps().tolist()          # I6
+    assert torch.equal(_build_labels(13), torch.arange(13) * 0.25)                    # I7
+    for eta in (0.0, 0.5):
+        ts, table = ddim_schedule(ac, 1000, 50, eta)
+        coefs = sampler.ddim_coefficients(ac, ts, eta)
+        for i, c in enumerate(coefs):
+            assert table[i, 0].item() == c["sqrt_ab"] and table[i, 1].item() == c["sqrt_1mab"]
+            assert bool(table[i, 5].item()) == c["last"]
+            if not c["last"]:
+                assert table[i, 2].item() == c["sqrt_abp"] and table[i, 3].item() == c["eps_coef"] and table[i, 4].item() == c["sigma"]
+    with pytest.raises(ValueError):
+        _build_labels(0)
+
+
+def test_unet_wrapper_errors(module):
+    with pytest.raises(ValueError):
+        module.unet(torch.zeros(1, 4, 8, 8), torch.zeros(1, dtype=torch.long), torch.zeros(1, 2, 3, 768))
+    with pytest.raises(NotImplementedError):
+        module._get_image_embeds(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(NotImplementedError):
+        bad = P.default_config()
+        bad.diffusion.noise_schedule = "cosine"
+        P.DiffusionModuleWithIP(bad, build_vae=False)
+
+
+def test_set_delta_scale(module):
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import _set_delta_scale_on_processors
+    _set_delta_scale_on_processors(module, 3.0)
+    vals = [p.delta_scale for p in module.unet.unet.attn_processors.values() if hasattr(p, "delta_scale")]
+    assert vals == [3.0] * 16
+
+
+def test_no_cpu_fallback(module):
+    from progressive_stable_diffusion_b200._lib import DaddError
+    with pytest.raises(DaddError):
+        module.ordinal_embedder(torch.tensor([1.0]))
+
+
+def test_shard_indices_cover_and_balance():
+    for n in (0, 1, 13, 104, 600):
+        for w in (1, 2, 4, 8):
+            parts = [parallel.shard_indices(n, r, w) for r in range(w)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_indices(4, 4, 4)
+
+
+def test_oracle_role_map_matches_product():
+    for n in cases.cross_attention_processor_names():
+        assert weights.role_of(n) == P.get_block_type(n)
+        assert oproc.frequency_mode_of(n) == P.get_frequency_mode_for_block(n)
