@@ -10,7 +10,7 @@
  *     synchronises, so every call is CUDA-graph capturable;
  *   - return 0 on success, non-zero on error (never throws); dadd_last_error() returns the message of the
  *     calling thread's last failure;
- *   - dtype codes: DADD_F32 = 0, DADD_BF16 = 1.
+ *   - dtype codes: DADD_F32 = 0, DADD_BF16 = 1, DADD_F16 = 2.
  */
 #ifndef DADD_B200_H
 #define DADD_B200_H
@@ -23,6 +23,7 @@ extern "C" {
 
 #define DADD_F32 0
 #define DADD_BF16 1
+#define DADD_F16 2 /* IEEE half: same tensor-core rate as bf16, 3 more mantissa bits (profiles/r01_precision_experiment.txt) */
 
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
@@ -91,28 +92,30 @@ int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, v
  * n_seg = 1, seg_len = 32, the single softmax of OrdinalIPAttnProcessor2_0.__call__
  * (src/models/attention_processor_base.py:96-118):
  *   o[b][n][h*d + :] = sum_s gates[s] * softmax(q_bh[n] . k_s^T * scale) v_s ,  s over n_seg segments of seg_len tokens
- * q: bf16 [B][N][*] with row stride q_stride elements, head h at column h*d (i.e. the to_q output as is);
- * k_cat, v_cat: bf16 [B][H][n_seg*seg_len][d] (step-invariant; projected once per sampling call, token order
+ * q: 16-bit (`dtype`) [B][N][*] with row stride q_stride elements, head h at column h*d (i.e. the to_q output as is);
+ * k_cat, v_cat: `dtype` [B][H][n_seg*seg_len][d] (step-invariant; projected once per sampling call, token order
  * dis | anat | delta = encoder_hidden_states[:, :16], [:, 16:32], [:, -16:], routing_gates.py:129-131);
  * gates: fp32[n_seg] ON DEVICE in token order (dis_gate, anat_gate, delta_scale);
- * o: bf16 [B][N][*] with row stride o_stride, written at column h*d (heads merged, ready for to_out).
+ * o: `dtype` [B][N][*] with row stride o_stride, written at column h*d (heads merged, ready for to_out).
  * d in {40, 80, 160} (d % 8 == 0, d <= 160); seg_len % 16 == 0; n_seg*seg_len <= 64.
  * delta_scale == 0 must be expressed as n_seg = 2 (the pathway is skipped, routing_gates.py:160,177).
  */
 int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
                         int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg, const float* gates,
-                        float scale, void* stream);
+                        float scale, int dtype /* DADD_BF16 | DADD_F16 */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Self-attention core (attn1): o = softmax(q k^T * scale) v per (b, h), no mask.
  * Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0, installed by
  * src/models/attention_processor_routing_gates.py:284-286 and attention_processor_base.py:196-197.
- * q, k, v: bf16 [B][N][*] with row strides (elements); head h at column h*d (so the three can alias one
- * fused [B][N][3C] projection output); o: bf16, same convention.  d in {40, 64, 80, 128, 160} (d % 8 == 0).
+ * q, k, v: 16-bit (`dtype`: DADD_BF16 | DADD_F16) [B][N][*] with row strides (elements); head h at column h*d (so the
+ * three can alias one fused [B][N][3C] projection output); o: same dtype and convention.  d % 8 == 0, d <= 160.
+ * impl: 0 = shape dispatch (N >= 128 -> tcgen05/TMEM/TMA flash kernel, else warp-level mma.sync kernel),
+ *       1 = force mma.sync, 2 = force tcgen05 (N >= 128 and d in {40, 64, 80, 128, 160} required).
  */
 int dadd_self_attn_fwd(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride,
                        int64_t v_stride, void* o, int64_t o_stride, int B, int H, int N, int d, float scale,
-                       void* stream);
+                       int dtype, int impl, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Feature Purifier pieces (src/models/feature_purifier.py:81-95), fp32 (runs once per sampling call).

@@ -22,8 +22,8 @@ SIGNATURES = {
     "dadd_groupnorm_fwd": [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P],
     "dadd_layernorm_fwd": [_P, _P, _P, _P, _L, _I, _F, _I, _P],
     "dadd_geglu_fwd": [_P, _P, _L, _I, _I, _P],
-    "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _P],
-    "dadd_self_attn_fwd": [_P, _P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _P],
+    "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _I, _P],
+    "dadd_self_attn_fwd": [_P, _P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P],
     "dadd_purifier_attn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dadd_purifier_gate_ln_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "dadd_aoe_interp_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],

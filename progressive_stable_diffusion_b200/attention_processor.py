@@ -16,7 +16,24 @@ import torch.nn.functional as F
 
 from . import ops, wcache
 
-COMPUTE_DTYPE = torch.bfloat16
+class _Compute:
+    """Element type of activations / GEMM operands on the device path.  bf16 is the configuration BASELINE.json names;
+    fp16 (the reference's own mixed-precision dtype, evaluation_pipeline.py:943) has the same tensor-core rate and 3 more
+    mantissa bits - needed for the 50-step PSNR gate with non-contractive random weights
+    (profiles/r01_precision_experiment.txt)."""
+    dtype = torch.bfloat16
+
+
+def set_compute_dtype(dtype: torch.dtype) -> None:
+    if dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("compute dtype must be torch.bfloat16 or torch.float16")
+    wcache.set_namespace(str(dtype))   # derived weights (fused QKV, cached K/V ...) are stored per compute dtype
+    _Compute.dtype = dtype
+
+
+def compute_dtype() -> torch.dtype:
+    return _Compute.dtype
+
 
 
 def _as_tokens(attn, hidden_states: torch.Tensor, temb):
@@ -35,9 +52,9 @@ def _as_tokens(attn, hidden_states: torch.Tensor, temb):
 
 def _finish(attn, out: torch.Tensor, residual: torch.Tensor, shape4, out_dtype: torch.dtype) -> torch.Tensor:
     """to_out[0] (+bias), to_out[1] = Dropout(0), optional reshape / residual / rescale (routing_gates.py:183-196)."""
-    w = wcache.cast(attn.to_out[0], "w", attn.to_out[0].weight, COMPUTE_DTYPE)
+    w = wcache.cast(attn.to_out[0], "w", attn.to_out[0].weight, compute_dtype())
     bias = attn.to_out[0].bias
-    bias = None if bias is None else wcache.cast(attn.to_out[0], "b", bias, COMPUTE_DTYPE)
+    bias = None if bias is None else wcache.cast(attn.to_out[0], "b", bias, compute_dtype())
     out = F.linear(out, w, bias)
     if shape4 is not None:
         b, c, h, w_ = shape4
@@ -68,18 +85,18 @@ class AttnProcessor2_0:
         residual = hidden_states
         out_dtype = hidden_states.dtype
         x, shape4 = _as_tokens(attn, hidden_states, temb)
-        x = x.to(COMPUTE_DTYPE)
+        x = x.to(compute_dtype())
         if not x.is_contiguous():
             x = x.contiguous()
         wqkv = wcache.get(attn, "wqkv", (attn.to_q.weight, attn.to_k.weight, attn.to_v.weight),
                           lambda: torch.cat([attn.to_q.weight, attn.to_k.weight, attn.to_v.weight], 0)
-                          .detach().to(COMPUTE_DTYPE).contiguous())
+                          .detach().to(compute_dtype()).contiguous())
         c = attn.to_q.weight.shape[0]
         bqkv = None
         if attn.to_q.bias is not None:
             bqkv = wcache.get(attn, "bqkv", (attn.to_q.bias, attn.to_k.bias, attn.to_v.bias),
                               lambda: torch.cat([attn.to_q.bias, attn.to_k.bias, attn.to_v.bias], 0)
-                              .detach().to(COMPUTE_DTYPE).contiguous())
+                              .detach().to(compute_dtype()).contiguous())
         qkv = F.linear(x, wqkv, bqkv)                              # (B, N, 3C): one GEMM
         o = ops.self_attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], attn.heads)
         return _finish(attn, o, residual, shape4, out_dtype)

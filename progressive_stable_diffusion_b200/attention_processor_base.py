@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops, wcache
-from .attention_processor import COMPUTE_DTYPE, AttnProcessor2_0, _as_tokens, _finish, _reject_mask
+from .attention_processor import AttnProcessor2_0, compute_dtype, _as_tokens, _finish, _reject_mask
 from .attention_processor_routing_gates import _hidden_size_of
 
 
@@ -48,7 +48,7 @@ class OrdinalIPAttnProcessor2_0(nn.Module):
             def fn():
                 p = F.linear(ehs.detach().to(w.dtype), w)
                 b, l, c = p.shape
-                return p.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(COMPUTE_DTYPE).contiguous()
+                return p.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(compute_dtype()).contiguous()
             return fn
 
         src = (ehs, attn.to_k.weight, attn.to_v.weight)
@@ -67,10 +67,10 @@ class OrdinalIPAttnProcessor2_0(nn.Module):
         elif getattr(attn, "norm_cross", None):
             raise NotImplementedError(
                 "Cross-attention with separate encoder hidden states is not implemented in OrdinalIPAttnProcessor2_0.")
-        x = x.to(COMPUTE_DTYPE)
+        x = x.to(compute_dtype())
         if not x.is_contiguous():
             x = x.contiguous()
-        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, COMPUTE_DTYPE))
+        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, compute_dtype()))
         k_cat, v_cat, length = self.project_kv(attn, encoder_hidden_states)
         one = wcache.get(self, "one", (attn.to_q.weight,), lambda: torch.ones(1, device=x.device, dtype=torch.float32))
         z = ops.cross_attention(q, k_cat, v_cat, one, attn.heads, length, 1)

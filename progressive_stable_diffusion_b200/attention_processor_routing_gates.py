@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops, wcache
-from .attention_processor import COMPUTE_DTYPE, AttnProcessor2_0, _as_tokens, _finish, _reject_mask
+from .attention_processor import AttnProcessor2_0, compute_dtype, _as_tokens, _finish, _reject_mask
 
 _ROLE_GATES: Dict[str, Tuple[float, float]] = {"anatomy": (0.5, 0.5), "disease": (0.5, 0.5), "both": (0.5, 0.5)}
 
@@ -85,7 +85,7 @@ class SplitInjectionAttentionProcessor(nn.Module):
                     parts.append(F.linear(e[:, -self.num_delta_tokens:, :], wd))
                 cat = torch.cat(parts, dim=1)                                   # (B, L, C)
                 b, l, c = cat.shape
-                return cat.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(COMPUTE_DTYPE).contiguous()
+                return cat.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(compute_dtype()).contiguous()
             return fn
 
         tag = f"kv{int(with_delta)}:{ehs.data_ptr()}:{tuple(ehs.shape)}"
@@ -119,10 +119,10 @@ class SplitInjectionAttentionProcessor(nn.Module):
         x, shape4 = _as_tokens(attn, hidden_states, temb)
         if encoder_hidden_states is None:
             encoder_hidden_states = x
-        x = x.to(COMPUTE_DTYPE)
+        x = x.to(compute_dtype())
         if not x.is_contiguous():
             x = x.contiguous()
-        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, COMPUTE_DTYPE))
+        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, compute_dtype()))
         k_cat, v_cat, n_seg = self.project_kv(attn, encoder_hidden_states)
         z = ops.cross_attention(q, k_cat, v_cat, self.gate_vector(), attn.heads, self.num_aoe_tokens, n_seg)
         return _finish(attn, z, residual, shape4, out_dtype)

@@ -3,30 +3,29 @@
 //   z = g_a softmax(Q Ka^T/sqrt d) Va + g_d softmax(Q Kd^T/sqrt d) Vd (+ lambda softmax(Q Kx^T/sqrt d) Vx)
 // and OrdinalIPAttnProcessor2_0.__call__ (src/models/attention_processor_base.py:96-118) as one 32-token segment.
 //
-// The whole K/V of one (sample, head) is <= 64 x 160 bf16 and lives in shared memory; each warp owns 16 query rows:
-// S = Q K_cat^T (one pass, all segments), an independent softmax per 16-token segment in registers, the gate of the
-// segment folded into the normalisation (invariant I11: sum_s g_s P_s V_s = [g_s P_s]_s V_cat), O = P V_cat.  No score
-// tensor is materialised; HBM traffic is Q in + O out (+ the tiny K/V), which is the roofline of this op (48 FLOP/B).
-// The contraction sizes (K = d <= 160, N = 48) are far below one tcgen05 tile, so the warp-level mma.sync path is used
-// here; the op is bound by HBM/L2 bytes, not by the tensor pipe.
+// The whole K/V of one (sample, head) is <= 64 x 160 16-bit elements and lives in shared memory; each warp owns 16
+// query rows: S = Q K_cat^T (one pass, all segments), an independent softmax per 16-token segment in registers, the
+// gate of the segment folded into the normalisation (invariant I11: sum_s g_s P_s V_s = [g_s P_s]_s V_cat), O = P V_cat.
+// No score tensor is materialised; HBM traffic is Q in + O out (+ the tiny K/V), which is the roofline of this op
+// (48 FLOP/B).  The contraction sizes (K = d <= 160, N = 48) are far below one tcgen05 tile, so the warp-level
+// mma.sync path is used here; the op is bound by HBM/L2 bytes, not by the tensor pipe.
 #include "mma_util.cuh"
 
 namespace daddk {
 
-template <int DK>
-__global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_stride,
-                                                         const __nv_bfloat16* __restrict__ k_cat,
-                                                         const __nv_bfloat16* __restrict__ v_cat,
-                                                         __nv_bfloat16* __restrict__ o, int64_t o_stride, int H, int N,
-                                                         int d, int seg_len, int n_seg, const float* __restrict__ gates,
+template <typename T, int DK>
+__global__ void __launch_bounds__(128) cross_attn_kernel(const T* __restrict__ q, int64_t q_stride,
+                                                         const T* __restrict__ k_cat, const T* __restrict__ v_cat,
+                                                         T* __restrict__ o, int64_t o_stride, int H, int N, int d,
+                                                         int seg_len, int n_seg, const float* __restrict__ gates,
                                                          float scale_log2e) {
     constexpr int QS = DK + 8;          // smem row stride (elements): conflict-free 32-bit fragment loads
     constexpr int LMAX = 64;
     constexpr int VS = LMAX + 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [64][QS]
-    __nv_bfloat16* Ks = Qs + 64 * QS;                                  // [LMAX][QS]
-    __nv_bfloat16* Vt = Ks + LMAX * QS;                                // [DK][VS]  (transposed V)
+    T* Qs = reinterpret_cast<T*>(smem_raw);   // [64][QS]
+    T* Ks = Qs + 64 * QS;                      // [LMAX][QS]
+    T* Vt = Ks + LMAX * QS;                    // [DK][VS]  (transposed V)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -35,9 +34,9 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __
     const int L = seg_len * n_seg;
     const int dv = d >> 3;              // 16-byte chunks per row
 
-    const __nv_bfloat16* qb = q + ((int64_t)b * N + row0) * q_stride + (int64_t)h * d;
-    const __nv_bfloat16* kb = k_cat + ((int64_t)(b * H + h) * L) * d;
-    const __nv_bfloat16* vb = v_cat + ((int64_t)(b * H + h) * L) * d;
+    const T* qb = q + ((int64_t)b * N + row0) * q_stride + (int64_t)h * d;
+    const T* kb = k_cat + ((int64_t)(b * H + h) * L) * d;
+    const T* vb = v_cat + ((int64_t)(b * H + h) * L) * d;
 
     constexpr int DKV = DK >> 3;
     for (int i = tid; i < 64 * DKV; i += 128) {
@@ -56,7 +55,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __
         const int r = i / dv, c = i % dv;      // token r, chunk c
         uint4 val = make_uint4(0, 0, 0, 0);
         if (r < L) val = *reinterpret_cast<const uint4*>(vb + (int64_t)r * d + c * 8);
-        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&val);
+        const T* e = reinterpret_cast<const T*>(&val);
 #pragma unroll
         for (int j = 0; j < 8; ++j) Vt[(c * 8 + j) * VS + r] = e[j];
     }
@@ -66,7 +65,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __
     float s[LMAX / 8][4];
 #pragma unroll
     for (int nt = 0; nt < LMAX / 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f; }
-    const __nv_bfloat16* qw = Qs + (warp * 16) * QS;
+    const T* qw = Qs + (warp * 16) * QS;
 #pragma unroll
     for (int kk = 0; kk < DK / 16; ++kk) {
         uint32_t a[4];
@@ -76,7 +75,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __
             if (nt * 8 < L) {
                 uint32_t b0, b1;
                 load_b_frag(b0, b1, Ks + (nt * 8) * QS, QS, kk * 16, g, t);
-                mma_bf16_16816(s[nt], a, b0, b1);
+                mma_16816<T>(s[nt], a, b0, b1);
             }
         }
     }
@@ -125,32 +124,32 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __
     for (int kk = 0; kk < LMAX / 16; ++kk) {
         if (kk * 16 < L) {
             uint32_t a[4];
-            a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-            a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-            a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+            a[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+            a[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+            a[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            a[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
             for (int nd = 0; nd < DK / 8; ++nd) {
                 if (nd < dv) {
                     uint32_t b0, b1;
                     load_b_frag(b0, b1, Vt + (nd * 8) * VS, VS, kk * 16, g, t);
-                    mma_bf16_16816(acc[nd], a, b0, b1);
+                    mma_16816<T>(acc[nd], a, b0, b1);
                 }
             }
         }
     }
     // ---- stage this warp's 16 x d tile in its own Q rows, then 16-byte coalesced stores -----------------------
     __syncwarp();
-    __nv_bfloat16* ow = Qs + (warp * 16) * QS;
+    T* ow = Qs + (warp * 16) * QS;
 #pragma unroll
     for (int nd = 0; nd < DK / 8; ++nd) {
         if (nd < dv) {
-            *reinterpret_cast<uint32_t*>(ow + g * QS + nd * 8 + 2 * t) = pack_bf16(acc[nd][0], acc[nd][1]);
-            *reinterpret_cast<uint32_t*>(ow + (g + 8) * QS + nd * 8 + 2 * t) = pack_bf16(acc[nd][2], acc[nd][3]);
+            *reinterpret_cast<uint32_t*>(ow + g * QS + nd * 8 + 2 * t) = pack2<T>(acc[nd][0], acc[nd][1]);
+            *reinterpret_cast<uint32_t*>(ow + (g + 8) * QS + nd * 8 + 2 * t) = pack2<T>(acc[nd][2], acc[nd][3]);
         }
     }
     __syncwarp();
-    __nv_bfloat16* ob = o + ((int64_t)b * N + row0 + warp * 16) * o_stride + (int64_t)h * d;
+    T* ob = o + ((int64_t)b * N + row0 + warp * 16) * o_stride + (int64_t)h * d;
     for (int i = lane; i < 16 * dv; i += 32) {
         const int r = i / dv, c = i % dv;
         if (row0 + warp * 16 + r < N)
@@ -158,20 +157,19 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const __nv_bfloat16* __
     }
 }
 
-template <int DK>
+template <typename T, int DK>
 static int launch_cross(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
                         int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg, const float* gates,
                         float scale, cudaStream_t s) {
-    const size_t smem = ((size_t)64 * (DK + 8) * 2 + (size_t)DK * 72) * sizeof(__nv_bfloat16);
-    auto kern = cross_attn_kernel<DK>;
+    const size_t smem = ((size_t)64 * (DK + 8) * 2 + (size_t)DK * 72) * sizeof(T);
+    auto kern = cross_attn_kernel<T, DK>;
     if (smem > 48 * 1024) {
         if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cross_attn smem"))
             return 2;
     }
     dim3 grid((N + 63) / 64, H, B);
-    kern<<<grid, 128, smem, s>>>((const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)k_cat,
-                                 (const __nv_bfloat16*)v_cat, (__nv_bfloat16*)o, o_stride, H, N, d, seg_len, n_seg, gates,
-                                 scale * 1.4426950408889634f);
+    kern<<<grid, 128, smem, s>>>((const T*)q, q_stride, (const T*)k_cat, (const T*)v_cat, (T*)o, o_stride, H, N, d, seg_len,
+                                 n_seg, gates, scale * 1.4426950408889634f);
     return launched("dadd_cross_attn_fwd");
 }
 
@@ -181,8 +179,9 @@ using namespace daddk;
 
 extern "C" int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
                                    int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg,
-                                   const float* gates, float scale, void* stream) {
+                                   const float* gates, float scale, int dtype, void* stream) {
     DADD_REQUIRE(q && k_cat && v_cat && o && gates, "dadd_cross_attn_fwd");
+    DADD_REQUIRE(dtype16_ok(dtype), "dadd_cross_attn_fwd");
     DADD_REQUIRE(B >= 0 && H > 0 && N >= 0 && B <= 65535 && H <= 65535, "dadd_cross_attn_fwd");
     DADD_REQUIRE(d > 0 && d % 8 == 0 && d <= 160, "dadd_cross_attn_fwd");
     DADD_REQUIRE(seg_len > 0 && seg_len % 16 == 0 && n_seg > 0 && seg_len * n_seg <= 64, "dadd_cross_attn_fwd");
@@ -191,11 +190,13 @@ extern "C" int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* 
     DADD_REQUIRE(((uintptr_t)q | (uintptr_t)k_cat | (uintptr_t)v_cat | (uintptr_t)o) % 16 == 0, "dadd_cross_attn_fwd");
     if (B == 0 || N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-#define DADD_X(DKV) return launch_cross<DKV>(q, q_stride, k_cat, v_cat, o, o_stride, B, H, N, d, seg_len, n_seg, gates, scale, s)
+#define DADD_X(DKV) \
+    DADD_DISPATCH_16(dtype, T, return (launch_cross<T, DKV>(q, q_stride, k_cat, v_cat, o, o_stride, B, H, N, d, seg_len, n_seg, gates, scale, s)))
     if (d <= 48) DADD_X(48);
     if (d <= 64) DADD_X(64);
     if (d <= 80) DADD_X(80);
     if (d <= 128) DADD_X(128);
     DADD_X(160);
 #undef DADD_X
+    return 1;
 }

@@ -14,11 +14,7 @@ struct DdimCoef {
 };
 
 template <typename T>
-__device__ __forceinline__ float ldf(const T* p, int64_t i);
-template <>
-__device__ __forceinline__ float ldf<float>(const float* p, int64_t i) { return p[i]; }
-template <>
-__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ldf(const T* p, int64_t i) { return to_f(p[i]); }
 
 // Each op rounds separately (the __f*_rn intrinsics are never contracted into FMAs) so the result is
 // bit-identical to the reference's chain of eager fp32 tensor ops.
@@ -108,7 +104,7 @@ using namespace daddk;
 
 extern "C" {
 
-int dadd_abi_version(void) { return 1; }
+int dadd_abi_version(void) { return 2; }
 const char* dadd_last_error(void) { return g_last_error; }
 int64_t dadd_launch_count(void) { return g_launches.load(); }
 void dadd_reset_launch_count(void) { g_launches.store(0); }
@@ -117,18 +113,13 @@ int dadd_ddim_step(float* x, const void* eps_cond, const void* eps_uncond, int e
                    float sqrt_ab_t, float sqrt_1mab_t, float sqrt_ab_prev, float eps_coef, float sigma,
                    const float* noise, float clampv, int is_last, int64_t n, void* stream) {
     DADD_REQUIRE(x && eps_cond && n >= 0, "dadd_ddim_step");
-    DADD_REQUIRE(eps_dtype == DADD_F32 || eps_dtype == DADD_BF16, "dadd_ddim_step");
+    DADD_REQUIRE(dtype_ok(eps_dtype), "dadd_ddim_step");
     DADD_REQUIRE(sqrt_ab_t != 0.0f, "dadd_ddim_step");
     if (n == 0) return 0;
     DdimCoef c{sqrt_ab_t, sqrt_1mab_t, sqrt_ab_prev, eps_coef, sigma, is_last};
     cudaStream_t s = (cudaStream_t)stream;
-    if (eps_dtype == DADD_F32)
-        ddim_kernel<float, false><<<grid_for(n, 256), 256, 0, s>>>(x, (const float*)eps_cond, (const float*)eps_uncond,
-                                                                    guidance, c, nullptr, nullptr, noise, clampv, n);
-    else
-        ddim_kernel<__nv_bfloat16, false><<<grid_for(n, 256), 256, 0, s>>>(
-            x, (const __nv_bfloat16*)eps_cond, (const __nv_bfloat16*)eps_uncond, guidance, c, nullptr, nullptr, noise,
-            clampv, n);
+    DADD_DISPATCH_ANY(eps_dtype, T, (ddim_kernel<T, false><<<grid_for(n, 256), 256, 0, s>>>(
+                                        x, (const T*)eps_cond, (const T*)eps_uncond, guidance, c, nullptr, nullptr, noise, clampv, n)));
     return launched("dadd_ddim_step");
 }
 
@@ -136,17 +127,12 @@ int dadd_ddim_step_table(float* x, const void* eps_cond, const void* eps_uncond,
                          const float* coef_table, const int32_t* step_state, const float* noise, float clampv,
                          int64_t n, void* stream) {
     DADD_REQUIRE(x && eps_cond && coef_table && step_state && n >= 0, "dadd_ddim_step_table");
-    DADD_REQUIRE(eps_dtype == DADD_F32 || eps_dtype == DADD_BF16, "dadd_ddim_step_table");
+    DADD_REQUIRE(dtype_ok(eps_dtype), "dadd_ddim_step_table");
     if (n == 0) return 0;
     DdimCoef c{};
     cudaStream_t s = (cudaStream_t)stream;
-    if (eps_dtype == DADD_F32)
-        ddim_kernel<float, true><<<grid_for(n, 256), 256, 0, s>>>(x, (const float*)eps_cond, (const float*)eps_uncond,
-                                                                   guidance, c, coef_table, step_state, noise, clampv, n);
-    else
-        ddim_kernel<__nv_bfloat16, true><<<grid_for(n, 256), 256, 0, s>>>(
-            x, (const __nv_bfloat16*)eps_cond, (const __nv_bfloat16*)eps_uncond, guidance, c, coef_table, step_state,
-            noise, clampv, n);
+    DADD_DISPATCH_ANY(eps_dtype, T, (ddim_kernel<T, true><<<grid_for(n, 256), 256, 0, s>>>(
+                                        x, (const T*)eps_cond, (const T*)eps_uncond, guidance, c, coef_table, step_state, noise, clampv, n)));
     return launched("dadd_ddim_step_table");
 }
 
@@ -161,12 +147,9 @@ int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64
 
 int dadd_image_post_fwd(const void* x, float* y, int64_t n, int dtype, void* stream) {
     DADD_REQUIRE(x && y && n >= 0, "dadd_image_post_fwd");
-    DADD_REQUIRE(dtype == DADD_F32 || dtype == DADD_BF16, "dadd_image_post_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_image_post_fwd");
     if (n == 0) return 0;
-    if (dtype == DADD_F32)
-        image_post_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, y, n);
-    else
-        image_post_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n);
+    DADD_DISPATCH_ANY(dtype, T, (image_post_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, n)));
     return launched("dadd_image_post_fwd");
 }
 

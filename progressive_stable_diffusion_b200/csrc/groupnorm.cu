@@ -21,9 +21,6 @@ namespace daddk {
 constexpr int GN_MAX_G = 64;
 constexpr int GN_CACHE = 12;  // cached 8-element vectors per thread
 
-__device__ __forceinline__ float to_f(float v) { return v; }
-__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
-
 struct Moments {
     float n, mean, m2;
 };
@@ -370,16 +367,12 @@ extern "C" int dadd_groupnorm_fwd(const void* x, const float* gamma, const float
     DADD_REQUIRE(x && y && gamma && beta, "dadd_groupnorm_fwd");
     DADD_REQUIRE(B >= 0 && C > 0 && HW > 0 && G > 0 && G <= GN_MAX_G, "dadd_groupnorm_fwd");
     DADD_REQUIRE(C % G == 0 && C % 8 == 0, "dadd_groupnorm_fwd");
-    DADD_REQUIRE(dtype == DADD_F32 || dtype == DADD_BF16, "dadd_groupnorm_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_groupnorm_fwd");
     DADD_REQUIRE(layout == DADD_LAYOUT_NCHW || layout == DADD_LAYOUT_NHWC, "dadd_groupnorm_fwd");
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (layout == DADD_LAYOUT_NHWC) {
-        if (dtype == DADD_BF16)
-            return launch_nhwc((const __nv_bfloat16*)x, gamma, beta, chan_add, chan_add_stride, (__nv_bfloat16*)y, B, C, HW, G, eps, apply_silu, s);
-        return launch_nhwc((const float*)x, gamma, beta, chan_add, chan_add_stride, (float*)y, B, C, HW, G, eps, apply_silu, s);
-    }
-    if (dtype == DADD_BF16)
-        return launch_nchw((const __nv_bfloat16*)x, gamma, beta, chan_add, chan_add_stride, (__nv_bfloat16*)y, B, C, HW, G, eps, apply_silu, s);
-    return launch_nchw((const float*)x, gamma, beta, chan_add, chan_add_stride, (float*)y, B, C, HW, G, eps, apply_silu, s);
+    if (layout == DADD_LAYOUT_NHWC)
+        DADD_DISPATCH_ANY(dtype, T, return launch_nhwc((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
+    DADD_DISPATCH_ANY(dtype, T, return launch_nchw((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
+    return 1;
 }

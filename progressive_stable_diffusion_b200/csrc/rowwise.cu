@@ -180,32 +180,23 @@ int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
                        int dtype, void* stream) {
     DADD_REQUIRE(x && y && gamma && beta && rows >= 0, "dadd_layernorm_fwd");
     DADD_REQUIRE(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 256, "dadd_layernorm_fwd");
-    DADD_REQUIRE(dtype == DADD_F32 || dtype == DADD_BF16, "dadd_layernorm_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_layernorm_fwd");
     if (rows == 0) return 0;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (dtype == DADD_BF16)
-        layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, rows, C, eps);
-    else
-        layernorm_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta, (float*)y,
-                                                                             rows, C, eps);
+    DADD_DISPATCH_ANY(dtype, T, (layernorm_kernel<T><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)y, rows, C, eps)));
     return launched("dadd_layernorm_fwd");
 }
 
 int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream) {
     DADD_REQUIRE(x && y && rows >= 0 && inner > 0 && inner % 8 == 0, "dadd_geglu_fwd");
-    DADD_REQUIRE(dtype == DADD_F32 || dtype == DADD_BF16, "dadd_geglu_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_geglu_fwd");
     if (rows == 0) return 0;
     const int64_t total = rows * (inner / 8);
     int64_t g = (total + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 16;
     if (g > cap) g = cap;
-    if (dtype == DADD_BF16)
-        geglu_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
-                                                                                   (__nv_bfloat16*)y, rows, inner);
-    else
-        geglu_kernel<float><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, rows, inner);
+    DADD_DISPATCH_ANY(dtype, T, (geglu_kernel<T><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, rows, inner)));
     return launched("dadd_geglu_fwd");
 }
 

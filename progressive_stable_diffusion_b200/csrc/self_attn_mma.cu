@@ -7,19 +7,19 @@
 
 namespace daddk {
 
-template <int DK>
-__global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16* __restrict__ q,
-                                                            const __nv_bfloat16* __restrict__ k,
-                                                            const __nv_bfloat16* __restrict__ v, int64_t q_stride,
+template <typename T, int DK>
+__global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict__ q,
+                                                            const T* __restrict__ k,
+                                                            const T* __restrict__ v, int64_t q_stride,
                                                             int64_t k_stride, int64_t v_stride,
-                                                            __nv_bfloat16* __restrict__ o, int64_t o_stride, int N,
+                                                            T* __restrict__ o, int64_t o_stride, int N,
                                                             int d, float scale_log2e) {
     constexpr int QS = DK + 8;
     constexpr int VS = 64 + 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [64][QS]
-    __nv_bfloat16* Ks = Qs + 64 * QS;                                  // [64][QS]
-    __nv_bfloat16* Vt = Ks + 64 * QS;                                  // [DK][VS]
+    T* Qs = reinterpret_cast<T*>(smem_raw);   // [64][QS]
+    T* Ks = Qs + 64 * QS;                                  // [64][QS]
+    T* Vt = Ks + 64 * QS;                                  // [DK][VS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -28,9 +28,9 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
     const int dv = d >> 3;
     constexpr int DKV = DK >> 3;
 
-    const __nv_bfloat16* qb = q + ((int64_t)b * N + row0) * q_stride + (int64_t)h * d;
-    const __nv_bfloat16* kb = k + ((int64_t)b * N) * k_stride + (int64_t)h * d;
-    const __nv_bfloat16* vb = v + ((int64_t)b * N) * v_stride + (int64_t)h * d;
+    const T* qb = q + ((int64_t)b * N + row0) * q_stride + (int64_t)h * d;
+    const T* kb = k + ((int64_t)b * N) * k_stride + (int64_t)h * d;
+    const T* vb = v + ((int64_t)b * N) * v_stride + (int64_t)h * d;
 
     for (int i = tid; i < 64 * DKV; i += 128) {
         const int r = i / DKV, c = i % DKV;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
     for (int nd = 0; nd < DK / 8; ++nd) { acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.0f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
 
-    const __nv_bfloat16* qw = Qs + (warp * 16) * QS;
+    const T* qw = Qs + (warp * 16) * QS;
     for (int kv0 = 0; kv0 < N; kv0 += 64) {
         __syncthreads();   // previous tile fully consumed (also orders the Q fill before first use)
         for (int i = tid; i < 64 * DKV; i += 128) {
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
             const int r = i / dv, c = i % dv;
             uint4 val = make_uint4(0, 0, 0, 0);
             if (kv0 + r < N) val = *reinterpret_cast<const uint4*>(vb + (int64_t)(kv0 + r) * v_stride + c * 8);
-            const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&val);
+            const T* e = reinterpret_cast<const T*>(&val);
 #pragma unroll
             for (int j = 0; j < 8; ++j) Vt[(c * 8 + j) * VS + r] = e[j];
         }
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
             for (int nt = 0; nt < 8; ++nt) {
                 uint32_t b0, b1;
                 load_b_frag(b0, b1, Ks + (nt * 8) * QS, QS, kk * 16, g, t);
-                mma_bf16_16816(s[nt], a, b0, b1);
+                mma_16816<T>(s[nt], a, b0, b1);
             }
         }
         if (kv0 + 64 > N) {   // mask the keys past the end of the sequence
@@ -113,16 +113,16 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             uint32_t a[4];
-            a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-            a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-            a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+            a[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+            a[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+            a[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            a[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
             for (int nd = 0; nd < DK / 8; ++nd) {
                 if (nd < dv) {
                     uint32_t b0, b1;
                     load_b_frag(b0, b1, Vt + (nd * 8) * VS, VS, kk * 16, g, t);
-                    mma_bf16_16816(acc[nd], a, b0, b1);
+                    mma_16816<T>(acc[nd], a, b0, b1);
                 }
             }
         }
@@ -131,16 +131,16 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
     l1 = quad_sum(l1);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
     __syncwarp();
-    __nv_bfloat16* ow = Qs + (warp * 16) * QS;   // this warp's Q rows are no longer needed by anyone else
+    T* ow = Qs + (warp * 16) * QS;   // this warp's Q rows are no longer needed by anyone else
 #pragma unroll
     for (int nd = 0; nd < DK / 8; ++nd) {
         if (nd < dv) {
-            *reinterpret_cast<uint32_t*>(ow + g * QS + nd * 8 + 2 * t) = pack_bf16(acc[nd][0] * i0, acc[nd][1] * i0);
-            *reinterpret_cast<uint32_t*>(ow + (g + 8) * QS + nd * 8 + 2 * t) = pack_bf16(acc[nd][2] * i1, acc[nd][3] * i1);
+            *reinterpret_cast<uint32_t*>(ow + g * QS + nd * 8 + 2 * t) = pack2<T>(acc[nd][0] * i0, acc[nd][1] * i0);
+            *reinterpret_cast<uint32_t*>(ow + (g + 8) * QS + nd * 8 + 2 * t) = pack2<T>(acc[nd][2] * i1, acc[nd][3] * i1);
         }
     }
     __syncwarp();
-    __nv_bfloat16* ob = o + ((int64_t)b * N + row0 + warp * 16) * o_stride + (int64_t)h * d;
+    T* ob = o + ((int64_t)b * N + row0 + warp * 16) * o_stride + (int64_t)h * d;
     for (int i = lane; i < 16 * dv; i += 32) {
         const int r = i / dv, c = i % dv;
         if (row0 + warp * 16 + r < N)
@@ -148,30 +148,31 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const __nv_bfloat16*
     }
 }
 
-template <int DK>
+template <typename T, int DK>
 static int launch_self_mma(const void* q, const void* k, const void* v, int64_t qs, int64_t ks, int64_t vs, void* o,
                            int64_t os, int B, int H, int N, int d, float scale, cudaStream_t s) {
-    const size_t smem = ((size_t)64 * (DK + 8) * 2 + (size_t)DK * 72) * sizeof(__nv_bfloat16);
-    auto kern = self_attn_mma_kernel<DK>;
+    const size_t smem = ((size_t)64 * (DK + 8) * 2 + (size_t)DK * 72) * sizeof(T);
+    auto kern = self_attn_mma_kernel<T, DK>;
     if (smem > 48 * 1024) {
         if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "self_attn smem"))
             return 2;
     }
     dim3 grid((N + 63) / 64, H, B);
-    kern<<<grid, 128, smem, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, qs, ks, vs,
-                                 (__nv_bfloat16*)o, os, N, d, scale * 1.4426950408889634f);
+    kern<<<grid, 128, smem, s>>>((const T*)q, (const T*)k, (const T*)v, qs, ks, vs,
+                                 (T*)o, os, N, d, scale * 1.4426950408889634f);
     return launched("dadd_self_attn_fwd(mma)");
 }
 
 int self_attn_mma(const void* q, const void* k, const void* v, int64_t qs, int64_t ks, int64_t vs, void* o, int64_t os,
-                  int B, int H, int N, int d, float scale, cudaStream_t s) {
-#define DADD_X(DKV) return launch_self_mma<DKV>(q, k, v, qs, ks, vs, o, os, B, H, N, d, scale, s)
+                  int B, int H, int N, int d, float scale, int dtype, cudaStream_t s) {
+#define DADD_X(DKV) DADD_DISPATCH_16(dtype, T, return (launch_self_mma<T, DKV>(q, k, v, qs, ks, vs, o, os, B, H, N, d, scale, s)))
     if (d <= 48) DADD_X(48);
     if (d <= 64) DADD_X(64);
     if (d <= 80) DADD_X(80);
     if (d <= 128) DADD_X(128);
     DADD_X(160);
 #undef DADD_X
+    return 1;
 }
 
 }  // namespace daddk

@@ -20,6 +20,7 @@ import torch
 from torch import Tensor
 
 from . import ops
+from .attention_processor import compute_dtype
 from .attention_processor_base import OrdinalIPAttnProcessor2_0
 from .attention_processor_routing_gates import SplitInjectionAttentionProcessor
 
@@ -187,7 +188,7 @@ def _engine_for(module, batch: int, sampling_steps: int, eta: float, do_cfg: boo
                 device: torch.device, steer_scale: float, use_graph: bool = True) -> ProgressionEngine:
     cache: Dict = module.__dict__.setdefault("_b200_engines", {})
     key = (batch, sampling_steps, float(eta), do_cfg, float(guidance_scale) if do_cfg else 0.0, tokens, str(device),
-           steer_scale != 0.0, use_graph, module.cfg.dataset.image_size)
+           steer_scale != 0.0, use_graph, module.cfg.dataset.image_size, str(compute_dtype()))
     eng = cache.get(key)
     if eng is None:
         eng = ProgressionEngine(module, batch, sampling_steps, eta, do_cfg, guidance_scale, tokens, device, use_graph)

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 NCHW, NHWC = 0, 1
 
 
@@ -22,7 +22,9 @@ def _dt(t: torch.Tensor) -> int:
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
-    raise TypeError(f"dadd kernels take float32 or bfloat16 tensors, got {t.dtype}")
+    if t.dtype == torch.float16:
+        return F16
+    raise TypeError(f"dadd kernels take float32, bfloat16 or float16 tensors, got {t.dtype}")
 
 
 def _cuda(*ts: Optional[torch.Tensor]) -> None:
@@ -138,27 +140,30 @@ def cross_attention(q: torch.Tensor, k_cat: torch.Tensor, v_cat: torch.Tensor, g
     _cuda(q, k_cat, v_cat, gates)
     b, n, c = q.shape
     d = c // heads
-    assert q.dtype == torch.bfloat16 and k_cat.dtype == torch.bfloat16 and v_cat.dtype == torch.bfloat16
+    assert q.dtype in (torch.bfloat16, torch.float16) and k_cat.dtype == q.dtype and v_cat.dtype == q.dtype
     assert k_cat.is_contiguous() and v_cat.is_contiguous() and k_cat.shape == (b, heads, seg_len * n_seg, d) == v_cat.shape
     assert gates.dtype == torch.float32 and gates.numel() >= n_seg
-    o = torch.empty(b, n, c, device=q.device, dtype=torch.bfloat16)
+    o = torch.empty(b, n, c, device=q.device, dtype=q.dtype)
     _lib.check(_lib.load().dadd_cross_attn_fwd(q.data_ptr(), _rows(q), k_cat.data_ptr(), v_cat.data_ptr(), o.data_ptr(), c,
                                                b, heads, n, d, seg_len, n_seg, gates.data_ptr(),
-                                               float(d ** -0.5 if scale is None else scale), _stream()),
+                                               float(d ** -0.5 if scale is None else scale), _dt(q), _stream()),
                "dadd_cross_attn_fwd")
     return o
 
 
-def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None) -> torch.Tensor:
-    """softmax(q k^T scale) v per head; q,k,v (B,N,H*d) bf16, possibly strided views of one fused QKV buffer."""
+def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+                   impl: str = "auto") -> torch.Tensor:
+    """softmax(q k^T scale) v per head; q,k,v (B,N,H*d) bf16/fp16, possibly strided views of one fused QKV buffer.
+    ``impl``: "auto" (N >= 128 -> tcgen05 kernel, else mma.sync kernel), "mma" or "tc"."""
     _cuda(q, k, v)
     b, n, c = q.shape
     d = c // heads
-    assert q.dtype == k.dtype == v.dtype == torch.bfloat16 and k.shape == q.shape == v.shape
-    o = torch.empty(b, n, c, device=q.device, dtype=torch.bfloat16)
+    assert q.dtype == k.dtype == v.dtype and q.dtype in (torch.bfloat16, torch.float16) and k.shape == q.shape == v.shape
+    o = torch.empty(b, n, c, device=q.device, dtype=q.dtype)
     _lib.check(_lib.load().dadd_self_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _rows(q), _rows(k), _rows(v),
                                               o.data_ptr(), c, b, heads, n, d,
-                                              float(d ** -0.5 if scale is None else scale), _stream()),
+                                              float(d ** -0.5 if scale is None else scale), _dt(q),
+                                              {"auto": 0, "mma": 1, "tc": 2}[impl], _stream()),
                "dadd_self_attn_fwd")
     return o
 

@@ -26,27 +26,27 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops, wcache
-from .attention_processor import COMPUTE_DTYPE, AttnProcessor2_0
+from .attention_processor import AttnProcessor2_0, compute_dtype
 
 CL = torch.channels_last
 
 
 # ----------------------------------------------------------------------------------------------- leaf helpers
 def _conv(mod: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    w = wcache.conv_filter(mod, "w", mod.weight, COMPUTE_DTYPE)
-    b = None if mod.bias is None else wcache.cast(mod, "b", mod.bias, COMPUTE_DTYPE)
+    w = wcache.conv_filter(mod, "w", mod.weight, compute_dtype())
+    b = None if mod.bias is None else wcache.cast(mod, "b", mod.bias, compute_dtype())
     return F.conv2d(x, w, b, mod.stride, mod.padding)
 
 
 def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
-    w = wcache.cast(mod, "w", mod.weight, COMPUTE_DTYPE)
-    b = None if mod.bias is None else wcache.cast(mod, "b", mod.bias, COMPUTE_DTYPE)
+    w = wcache.cast(mod, "w", mod.weight, compute_dtype())
+    b = None if mod.bias is None else wcache.cast(mod, "b", mod.bias, compute_dtype())
     return F.linear(x, w, b)
 
 
 def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor) -> torch.Tensor:
-    w = wcache.get(mod, "w2d", (mod.weight,), lambda: mod.weight.detach().to(COMPUTE_DTYPE).reshape(mod.out_channels, -1).contiguous())
-    b = wcache.cast(mod, "b", mod.bias, COMPUTE_DTYPE)
+    w = wcache.get(mod, "w2d", (mod.weight,), lambda: mod.weight.detach().to(compute_dtype()).reshape(mod.out_channels, -1).contiguous())
+    b = wcache.cast(mod, "b", mod.bias, compute_dtype())
     return F.linear(tokens, w, b)
 
 
@@ -326,7 +326,7 @@ class UNet2DConditionModel(nn.Module):
         terms = self._split_terms(time_terms)
         ehs = encoder_hidden_states
 
-        x = sample.to(COMPUTE_DTYPE).contiguous(memory_format=CL)
+        x = sample.to(compute_dtype()).contiguous(memory_format=CL)
         x = _conv(self.conv_in, x)
         skips = [x]
         for blk in self.down_blocks:

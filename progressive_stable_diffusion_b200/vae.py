@@ -70,8 +70,8 @@ class AutoencoderKL(nn.Module):
         self.config = SimpleNamespace(latent_channels=4, scaling_factor=0.18215)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True):
-        from .attention_processor import COMPUTE_DTYPE
-        x = z.to(COMPUTE_DTYPE).contiguous(memory_format=CL)
+        from .attention_processor import compute_dtype
+        x = z.to(compute_dtype()).contiguous(memory_format=CL)
         img = self.decoder(_conv(self.post_quant_conv, x))
         return SimpleNamespace(sample=img) if return_dict else (img,)
 

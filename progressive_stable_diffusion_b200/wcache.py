@@ -29,8 +29,16 @@ def _drop(owner_id: int) -> None:
     _FINALIZERS.pop(owner_id, None)
 
 
+_NAMESPACE = [""]
+
+
+def set_namespace(ns: str) -> None:
+    """Entries built under different compute dtypes coexist (captured graphs of either keep their tensors alive)."""
+    _NAMESPACE[0] = ns
+
+
 def get(owner: object, tag: str, sources: Sequence[torch.Tensor], build: Callable[[], torch.Tensor]) -> torch.Tensor:
-    key = (id(owner), tag)
+    key = (id(owner), tag, _NAMESPACE[0])
     stamp = _stamp(sources)
     hit = _CACHE.get(key)
     if hit is not None and hit[0] == stamp:

@@ -51,11 +51,11 @@ def test_ctypes_table_covers_the_header(lib):
 
 def test_abi_version_and_error_channel(lib):
     l = lib.load()
-    assert l.dadd_abi_version() == 1
+    assert l.dadd_abi_version() == 2
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = l.dadd_groupnorm_fwd(None, None, None, None, 0, None, 1, 320, 64, 32, 1e-5, 1, 1, 1, None)
     assert rc != 0 and b"dadd_groupnorm_fwd" in l.dadd_last_error()
-    rc = l.dadd_cross_attn_fwd(1, 320, 1, 1, 1, 320, 1, 8, 64, 41, 16, 3, 1, 0.1, None)
+    rc = l.dadd_cross_attn_fwd(1, 320, 1, 1, 1, 320, 1, 8, 64, 41, 16, 3, 1, 0.1, 1, None)
     assert rc != 0 and b"d % 8" in l.dadd_last_error()
 
 
