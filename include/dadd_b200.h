@@ -28,7 +28,7 @@ extern "C" {
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
 
-/* ABI version of this header (bumped on any signature change). */
+/* ABI version of this header (bumped on any signature change; currently 3). */
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -72,15 +72,35 @@ int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64
  *   y = act(GroupNorm_G(x + chan_add[b * chan_add_stride + c]; eps) * gamma[c] + beta[c]),  act = SiLU or identity.
  * Statistics in fp32 (shifted sums + Chan combine).  x/y: `dtype`; gamma/beta/chan_add: fp32.
  * C % G == 0 and C % 8 == 0 required; for NHWC additionally (C/8) <= 512.
+ * NHWC: samples up to ~1.5 MB with >= 8 channels per group (every UNet site) run as ONE launch - a thread-block cluster
+ * per sample stages its slab in shared memory and combines statistics through distributed shared memory; larger
+ * samples (the VAE decoder) run as flat passes (partial statistics per pixel chunk, finalise, normalise; the second read
+ * of x comes from L2).  Callers always pass `workspace`: at least dadd_groupnorm_workspace_bytes(B, C, HW, G, layout) bytes of device memory,
+ * 16-byte aligned, borrowed until the queued work has run.  NCHW needs none (0 bytes, NULL allowed).
  */
+int64_t dadd_groupnorm_workspace_bytes(int B, int C, int HW, int G, int layout);
 int dadd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* chan_add /* nullable */,
                        int64_t chan_add_stride /* elements between samples */, void* y, int B, int C, int HW, int G, float eps, int apply_silu, int layout, int dtype,
-                       void* stream);
+                       void* workspace /* nullable for NCHW */, int64_t workspace_bytes, void* stream);
 
 /* LayerNorm over the last dimension (the 48 LayerNorms of the BasicTransformerBlocks and the three of
  * src/models/feature_purifier.py:46-47,62).  x,y: [rows][C] `dtype`; gamma/beta fp32; C % 8 == 0, C <= 2048. */
 int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps,
                        int dtype, void* stream);
+
+/* Residual add fused with the LayerNorm that consumes it (BasicTransformerBlock: hidden = attn(...) + hidden;
+ * norm_hidden = norm(hidden)):  s = x + r rounded to `dtype` (stored to sum_out when non-NULL),
+ * y = LayerNorm(s) * gamma + beta.  Same shapes / limits as dadd_layernorm_fwd; x, r, sum_out, y: [rows][C]. */
+int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out /* nullable */, const float* gamma, const float* beta,
+                           void* y, int64_t rows, int C, float eps, int dtype, void* stream);
+
+/* Channel bias and/or residual add in one vectorised pass: y[r][c] = a[r][c] (+ res[r][c]) (+ bias[c]).
+ * Replaces the bias add after a library convolution and the residual adds of ResnetBlock2D / Transformer2DModel /
+ * the feed-forward (diffusers graph reached through src/models/unet/unet.py:140-146).  a, res, y: [rows][C] `dtype`
+ * (NHWC activations viewed as rows of C channels, or token matrices); bias: fp32 [C]; at least one of res, bias.
+ * y may alias a or res.  C % 8 == 0. */
+int dadd_bias_residual_fwd(const void* a, const void* res /* nullable */, const float* bias /* nullable */, void* y,
+                           int64_t rows, int C, int dtype, void* stream);
 
 /* GEGLU gate of the transformer feed-forward: y[r][j] = x[r][j] * gelu_erf(x[r][inner + j]), x: [rows][2*inner]. */
 int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream);

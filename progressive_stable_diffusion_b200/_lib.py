@@ -19,8 +19,11 @@ SIGNATURES = {
     "dadd_ddim_step": [_P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _P, _F, _I, _L, _P],
     "dadd_ddim_step_table": [_P, _P, _P, _I, _F, _P, _P, _P, _F, _L, _P],
     "dadd_step_begin": [_P, _P, _P, _L, _P],
-    "dadd_groupnorm_fwd": [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P],
+    "dadd_groupnorm_workspace_bytes": [_I, _I, _I, _I, _I],
+    "dadd_groupnorm_fwd": [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P, _L, _P],
     "dadd_layernorm_fwd": [_P, _P, _P, _P, _L, _I, _F, _I, _P],
+    "dadd_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
+    "dadd_bias_residual_fwd": [_P, _P, _P, _P, _L, _I, _I, _P],
     "dadd_geglu_fwd": [_P, _P, _L, _I, _I, _P],
     "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _I, _P],
     "dadd_self_attn_fwd": [_P, _P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P],
@@ -51,7 +54,7 @@ def load() -> ctypes.CDLL:
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = c_int
+        fn.restype = c_int64 if name.endswith("_bytes") else c_int
     lib.dadd_abi_version.restype = c_int
     lib.dadd_last_error.restype = c_char_p
     lib.dadd_launch_count.restype = c_int64

@@ -2,19 +2,13 @@
 // Reference ops: diffusers ResnetBlock2D.norm1/norm2 + SiLU, conv_norm_out + conv_act, Transformer2DModel.norm
 // (reached via src/models/unet/unet.py:140-146).
 //
-// NHWC (channels-last, the layout the B200 UNet runs in): a thread-block cluster of S CTAs covers one sample, each CTA
-// owns HW/S pixels x all C channels (fully coalesced 16 B accesses).  Every thread keeps a fixed 8-channel column, so
-// per-channel shifted sums live in registers; per-channel -> per-group -> per-cluster combination uses Chan's
-// formula (no E[x^2]-E[x]^2 cancellation), the cross-CTA hop goes through distributed shared memory.
-// The CTA's slab stays in registers between the statistics pass and the normalise pass when it fits.
+// NHWC (channels-last, the layout the B200 UNet runs in): flat, fully parallel passes (partial statistics, a tiny
+// finalise, then normalise) whose grids fill all 148 SMs; the second pass re-reads the activation from the 126 MB L2, so
+// HBM sees one read and one write.  Every thread keeps a fixed 8-channel column (coalesced 16 B accesses, per-channel scale/shift in registers).
 // NCHW (the reference's layout): a group is contiguous, one CTA per (sample, group).
-#include <cooperative_groups.h>
-
 #include <cstdlib>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace daddk {
 
@@ -38,159 +32,487 @@ __device__ __forceinline__ Moments chan_combine(Moments a, Moments b) {
 }
 
 // ------------------------------------------------------------------------------------------------ NHWC
-template <typename T, bool CACHED>
-__global__ void __launch_bounds__(512) gn_nhwc_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta,
-                                                      const float* __restrict__ chan_add, int64_t add_stride, T* __restrict__ y, int HW,
-                                                      int C, int G, float eps, int apply_silu, int cluster_size) {
-    extern __shared__ float smem[];
-    __shared__ float cta_stats[GN_MAX_G * 3];
-    __shared__ float grp[GN_MAX_G * 2];
+// Three lean launches over x[b][pixel][channel], each with ONE global-memory round trip on its critical path:
+//   gn_stats_nhwc:  CTA = (pixel chunk, sample); thread = fixed 8-channel column x pixel phase.  Shifted sums
+//                   sum(v - K_g), sum((v - K_g)^2) with one shift per (sample, group) -- K_g = the group's first channel
+//                   at pixel 0 -- so that the partials of different chunks simply add.  Out: part[b][chunk][g] (float2).
+//   gn_final:       one CTA per sample: partials -> (mean, rstd) per group -> per-channel scale / shift
+//                   coef[b][0][c] = rstd * gamma[c],  coef[b][1][c] = beta[c] + (chan_add[b][c] - mean) * rstd * gamma[c].
+//   gn_apply_nhwc:  flat pass  y = act(x * scale + shift); x is re-read from L2 (a whole activation is <= 50 MB).
+// No atomics anywhere: results are bit-reproducible run to run.
+struct GnPlan {
+    int V, PH, threads, npx, chunks;
+};
 
-    const int V = C >> 3;                 // 8-channel vectors per pixel
-    const int PH = blockDim.x / V;        // pixel phases per CTA
-    const int tid = threadIdx.x;
-    const int v = tid % V, ph = tid / V;
-    const int c0 = v << 3;
-    const int b = blockIdx.y;
-    const int rank = blockIdx.x;          // == rank in cluster (cluster spans gridDim.x)
-    const int npix = HW / cluster_size;
-    const int p0 = rank * npix;
-    const int cpg = C / G;
+static GnPlan gn_plan(int B, int C, int HW) {
+    GnPlan p;
+    p.V = C >> 3;
+    p.PH = 512 / p.V;
+    if (p.PH < 1) p.PH = 1;
+    if (p.PH > HW) p.PH = HW;
+    p.threads = p.V * p.PH;
+    p.npx = p.PH * 16;                                  // up to 16 vectors (256 B) per thread ...
+    if (p.npx > HW) p.npx = HW;
+    p.chunks = (HW + p.npx - 1) / p.npx;
+    const int want = num_sms() + num_sms() / 2;         // ... unless that leaves SMs idle
+    while ((int64_t)p.chunks * B < want && p.npx > p.PH) {
+        p.npx = (p.npx / 2 < p.PH) ? p.PH : p.npx / 2;
+        p.chunks = (HW + p.npx - 1) / p.npx;
+    }
+    return p;
+}
 
-    float* s1 = smem;                     // [PH][C]
-    float* s2 = smem + (size_t)PH * C;    // [PH][C]
-    float* ksh = s2 + (size_t)PH * C;     // [C]
-
-    const T* xb = x + ((size_t)b * HW + p0) * C + c0;
-    T* yb = y + ((size_t)b * HW + p0) * C + c0;
-
-    float add[8];
+template <typename T>
+__global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict__ x, const float* __restrict__ chan_add,
+                                                            int64_t add_stride, float2* __restrict__ part, int HW, int C, int G,
+                                                            int npx) {
+    extern __shared__ float smem[];      // [PH][C] x 2
+    const int V = C >> 3, PH = blockDim.x / V;
+    const int tid = threadIdx.x, v = tid % V, ph = tid / V, c0 = v << 3;
+    const int b = blockIdx.y, chunk = blockIdx.x, cpg = C / G;
+    const T* xs = x + (size_t)b * HW * C;
+    const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
+    const int p0 = chunk * npx, p1 = min(HW, p0 + npx);
+    const T* xp = xs + c0;
+    int p = p0 + ph;
+    // first batch of loads goes out before anything else
+    constexpr int U = 4;
+    Vec8<T> t[U];
+    const bool full0 = p + (U - 1) * PH < p1;
+    if (full0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) add[i] = chan_add ? chan_add[(size_t)b * add_stride + c0 + i] : 0.0f;
-
-    float K[8], a1[8], a2[8];
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+    }
+    float sh[8];                                        // chan_add[c] - K_g(c),  K_g = x[b][0][g*cpg] + chan_add[g*cpg]
     {
-        Vec8<T> k;
-        k.load(xb);
-        k.unpack(K);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { K[i] += add[i]; a1[i] = 0.0f; a2[i] = 0.0f; }
-    }
-
-    Vec8<T> cache[CACHED ? GN_CACHE : 1];
-    if (CACHED) {
-#pragma unroll
-        for (int j = 0; j < GN_CACHE; ++j) {
-            const int p = ph + j * PH;
-            if (p < npix) cache[j].load(xb + (size_t)p * C);
-        }
-#pragma unroll
-        for (int j = 0; j < GN_CACHE; ++j) {
-            const int p = ph + j * PH;
-            if (p < npix) {
-                float f[8];
-                cache[j].unpack(f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const float d = f[i] + add[i] - K[i]; a1[i] += d; a2[i] += d * d; }
-            }
-        }
-    } else {
-        for (int p = ph; p < npix; p += PH) {
-            Vec8<T> t;
-            t.load(xb + (size_t)p * C);
-            float f[8];
-            t.unpack(f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = f[i] + add[i] - K[i]; a1[i] += d; a2[i] += d * d; }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        s1[(size_t)ph * C + c0 + i] = a1[i];
-        s2[(size_t)ph * C + c0 + i] = a2[i];
-        if (ph == 0) ksh[c0 + i] = K[i];
-    }
-    __syncthreads();
-
-    // per-channel moments of this CTA's slab (overwrite row 0 of s1/s2 with mean / M2)
-    for (int c = tid; c < C; c += blockDim.x) {
-        float t1 = 0.0f, t2 = 0.0f;
-        for (int q = 0; q < PH; ++q) { t1 += s1[(size_t)q * C + c]; t2 += s2[(size_t)q * C + c]; }
-        const float n = (float)npix;
-        const float m = t1 / n;
-        s1[c] = ksh[c] + m;            // in place: column c is touched by this thread only
-        s2[c] = fmaxf(t2 - t1 * m, 0.0f);
-    }
-    __syncthreads();
-
-    if (tid < G) {
-        float mg = 0.0f;
-        for (int i = 0; i < cpg; ++i) mg += s1[tid * cpg + i];
-        mg /= (float)cpg;
-        float m2 = 0.0f;
-        for (int i = 0; i < cpg; ++i) {
-            const float d = s1[tid * cpg + i] - mg;
-            m2 += s2[tid * cpg + i] + (float)npix * d * d;
-        }
-        cta_stats[tid * 3 + 0] = (float)npix * (float)cpg;
-        cta_stats[tid * 3 + 1] = mg;
-        cta_stats[tid * 3 + 2] = m2;
-    }
-    if (cluster_size > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cluster.sync();
-        if (tid < G) {
-            Moments acc{0.0f, 0.0f, 0.0f};
-            for (int r = 0; r < cluster_size; ++r) {
-                const float* rs = cluster.map_shared_rank(cta_stats, r);
-                acc = chan_combine(acc, Moments{rs[tid * 3], rs[tid * 3 + 1], rs[tid * 3 + 2]});
-            }
-            grp[tid * 2] = acc.mean;
-            grp[tid * 2 + 1] = rsqrtf(acc.m2 / acc.n + eps);
-        }
-        cluster.sync();
-    } else {
-        __syncthreads();
-        if (tid < G) {
-            grp[tid * 2] = cta_stats[tid * 3 + 1];
-            grp[tid * 2 + 1] = rsqrtf(cta_stats[tid * 3 + 2] / cta_stats[tid * 3] + eps);
-        }
-        __syncthreads();
-    }
-
-    float sa[8], sb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i, g = c / cpg;
-        const float a = grp[g * 2 + 1] * gamma[c];
-        sa[i] = a;
-        sb[i] = beta[c] + (add[i] - grp[g * 2]) * a;
-    }
-    auto emit = [&](Vec8<T>& t, int p) {
-        float f[8];
-        t.unpack(f);
+        int g = c0 / cpg, r = c0 - g * cpg;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float o = fmaf(f[i], sa[i], sb[i]);
-            f[i] = apply_silu ? silu(o) : o;
-        }
-        t.pack(f);
-        t.store(yb + (size_t)p * C);
-    };
-    if (CACHED) {
-#pragma unroll
-        for (int j = 0; j < GN_CACHE; ++j) {
-            const int p = ph + j * PH;
-            if (p < npix) emit(cache[j], p);
-        }
-    } else {
-        for (int p = ph; p < npix; p += PH) {
-            Vec8<T> t;
-            t.load(xb + (size_t)p * C);
-            emit(t, p);
+            const int cg = g * cpg;
+            const float k = to_f(xs[cg]) + (addb ? addb[cg] : 0.0f);
+            sh[i] = (addb ? addb[c0 + i] : 0.0f) - k;
+            if (++r == cpg) { r = 0; ++g; }
         }
     }
+    float a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a1[i] = 0.0f; a2[i] = 0.0f; }
+    auto acc = [&](const Vec8<T>& tv) {
+        float f[8];
+        tv.unpack(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = f[i] + sh[i]; a1[i] += d; a2[i] = fmaf(d, d, a2[i]); }
+    };
+    if (full0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc(t[u]);
+        p += U * PH;
+    }
+    for (; p + (U - 1) * PH < p1; p += U * PH) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc(t[u]);
+    }
+    for (; p < p1; p += PH) {
+        t[0].load(xp + (size_t)p * C);
+        acc(t[0]);
+    }
+    float* s1 = smem;
+    float* s2 = smem + (size_t)PH * C;
+    *reinterpret_cast<float4*>(s1 + (size_t)ph * C + c0) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+    *reinterpret_cast<float4*>(s1 + (size_t)ph * C + c0 + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+    *reinterpret_cast<float4*>(s2 + (size_t)ph * C + c0) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+    *reinterpret_cast<float4*>(s2 + (size_t)ph * C + c0 + 4) = make_float4(a2[4], a2[5], a2[6], a2[7]);
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {         // pixel phases -> one (sum, sumsq) per channel
+        float t1 = 0.0f, t2 = 0.0f;
+        for (int q = 0; q < PH; ++q) { t1 += s1[(size_t)q * C + c]; t2 += s2[(size_t)q * C + c]; }
+        s1[c] = t1;
+        s2[c] = t2;
+    }
+    __syncthreads();
+    if (tid < G) {
+        float t1 = 0.0f, t2 = 0.0f;
+        for (int i = 0; i < cpg; ++i) { t1 += s1[tid * cpg + i]; t2 += s2[tid * cpg + i]; }
+        part[((size_t)b * gridDim.x + chunk) * G + tid] = make_float2(t1, t2);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_final_kernel(const float2* __restrict__ part, const T* __restrict__ x,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ chan_add, int64_t add_stride,
+                                                       float* __restrict__ coef, int chunks, int HW, int C, int G, float eps) {
+    __shared__ float2 grp[GN_MAX_G];
+    const int b = blockIdx.x, tid = threadIdx.x, cpg = C / G;
+    const T* xs = x + (size_t)b * HW * C;
+    const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
+    if (tid < G) {
+        float t1 = 0.0f, t2 = 0.0f;
+        for (int k = 0; k < chunks; ++k) {
+            const float2 w = part[((size_t)b * chunks + k) * G + tid];
+            t1 += w.x;
+            t2 += w.y;
+        }
+        const float inv_n = __fdividef(1.0f, (float)cpg * (float)HW);
+        const float m = t1 * inv_n;
+        const float var = fmaxf(t2 - t1 * m, 0.0f) * inv_n;
+        const int cg = tid * cpg;
+        grp[tid] = make_float2(to_f(xs[cg]) + (addb ? addb[cg] : 0.0f) + m, rsqrtf(var + eps));
+    }
+    __syncthreads();
+    float* sc = coef + (size_t)b * 2 * C;
+    for (int c = tid; c < C; c += blockDim.x) {
+        const float2 st = grp[c / cpg];
+        const float a = st.y * gamma[c];
+        sc[c] = a;
+        sc[C + c] = beta[c] + ((addb ? addb[c] : 0.0f) - st.x) * a;
+    }
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// act: 0 = identity, 1 = SiLU as o / (1 + exp(-o)) (two MUFU ops per element), 2 = SiLU as h + h * tanh(h) with h = o / 2
+// (one MUFU op; the caller passes scale / shift already halved, so the kernel computes h directly).
+template <typename T>
+__device__ __forceinline__ void gn_emit(Vec8<T>& t, const float (&sa)[8], const float (&sb)[8], int act, T* dst) {
+    float f[8];
+    t.unpack(f);
+    if (act == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float h = fmaf(f[i], sa[i], sb[i]);
+            f[i] = fmaf(h, tanh_approx(h), h);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float o = fmaf(f[i], sa[i], sb[i]);
+            f[i] = act ? silu(o) : o;
+        }
+    }
+    t.pack(f);
+    t.store(dst);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) gn_apply_nhwc_kernel(const T* __restrict__ x, const float* __restrict__ coef,
+                                                            T* __restrict__ y, int HW, int C, int apply_silu, int npx) {
+    const int V = C >> 3, PH = blockDim.x / V;
+    const int tid = threadIdx.x, v = tid % V, ph = tid / V, c0 = v << 3;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int p0 = chunk * npx, p1 = min(HW, p0 + npx);
+    const T* xp = x + (size_t)b * HW * C + c0;
+    T* yp = y + (size_t)b * HW * C + c0;
+    const float* sc = coef + (size_t)b * 2 * C + c0;
+    int p = p0 + ph;
+    constexpr int U = 4;
+    Vec8<T> t[U];
+    const bool full0 = p + (U - 1) * PH < p1;
+    if (full0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+    }
+    float sa[8], sb[8];
+    {
+        const float4 a0 = *reinterpret_cast<const float4*>(sc), a1 = *reinterpret_cast<const float4*>(sc + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sc + C), b1 = *reinterpret_cast<const float4*>(sc + C + 4);
+        sa[0] = a0.x; sa[1] = a0.y; sa[2] = a0.z; sa[3] = a0.w; sa[4] = a1.x; sa[5] = a1.y; sa[6] = a1.z; sa[7] = a1.w;
+        sb[0] = b0.x; sb[1] = b0.y; sb[2] = b0.z; sb[3] = b0.w; sb[4] = b1.x; sb[5] = b1.y; sb[6] = b1.z; sb[7] = b1.w;
+        if (apply_silu == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sa[i] *= 0.5f; sb[i] *= 0.5f; }
+        }
+    }
+    if (full0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) gn_emit(t[u], sa, sb, apply_silu, yp + (size_t)(p + u * PH) * C);
+        p += U * PH;
+    }
+    for (; p + (U - 1) * PH < p1; p += U * PH) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+#pragma unroll
+        for (int u = 0; u < U; ++u) gn_emit(t[u], sa, sb, apply_silu, yp + (size_t)(p + u * PH) * C);
+    }
+    for (; p < p1; p += PH) {
+        t[0].load(xp + (size_t)p * C);
+        gn_emit(t[0], sa, sb, apply_silu, yp + (size_t)p * C);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ NHWC, one launch
+// Samples up to ~1.6 MB (every GroupNorm of the UNet): a thread-block cluster of S <= 8 CTAs owns one sample, CTA r the
+// contiguous slab of pixels [r*npix, (r+1)*npix).  The slab is pulled into shared memory ONCE with bulk async copies
+// (cp.async.bulk + mbarrier: no registers spent on loads in flight), statistics are taken from shared memory, the
+// per-group partials of the S CTAs are combined through distributed shared memory (two cluster barriers, no global round
+// trip), and the normalise pass reads the slab back from shared memory: HBM/L2 sees one read and one write, one launch.
+// Pixels beyond the shared-memory budget (only the 960-channel 32x32 site) are streamed from L2 in both passes.
+// Needs channels-per-group >= 8 so that a thread's 8 channels touch at most two groups.
+constexpr int GNC_THREADS = 512;
+constexpr int GNC_SLAB_BUDGET = 96 * 1024;              // two CTAs per SM
+
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    const float* __restrict__ chan_add, int64_t add_stride,
+                                                                    T* __restrict__ y, int HW, int C, int G, float eps,
+                                                                    int apply_silu, int npix, int spix, int S) {
+    extern __shared__ __align__(128) unsigned char gn_smem[];
+    const int V = C >> 3, PH = blockDim.x / V;
+    const int tid = threadIdx.x, v = tid % V, ph = tid / V, c0 = v << 3;
+    const int b = blockIdx.y, rank = blockIdx.x, cpg = C / G;
+    const size_t slab_bytes = (size_t)spix * C * sizeof(T);
+    T* slab = reinterpret_cast<T*>(gn_smem);
+    float4* red = reinterpret_cast<float4*>(gn_smem + ((slab_bytes + 127) & ~(size_t)127));   // [PH][V]: {A1, A2, B1, B2}
+    float2* part = reinterpret_cast<float2*>(red + (size_t)PH * V);                            // [G] this CTA's partials
+    float2* grp = part + GN_MAX_G;                                                             // [G] (mean, rstd)
+    float* Kg = reinterpret_cast<float*>(grp + GN_MAX_G);                                      // [G] shifts
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(Kg + GN_MAX_G);
+
+    const T* xs = x + (size_t)b * HW * C;
+    const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
+    const int p0 = rank * npix;
+    const int my = max(0, min(npix, HW - p0));          // pixels of this CTA
+    const int ms = min(my, spix);                       // ... of which staged in shared memory
+    const T* xg = xs + (size_t)p0 * C;
+    T* yg = y + ((size_t)b * HW + p0) * C;
+
+    if (tid == 0) {      // the slab copy goes out first: everything else overlaps with it
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gn_smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t total = (uint32_t)((size_t)ms * C * sizeof(T));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gn_smem_u32(mbar)), "r"(total) : "memory");
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            const uint32_t n = min(32768u, total - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(gn_smem_u32(gn_smem + off)), "l"(reinterpret_cast<const unsigned char*>(xg) + off), "r"(n),
+                           "r"(gn_smem_u32(mbar))
+                         : "memory");
+        }
+    }
+    if (tid < G) Kg[tid] = to_f(xs[tid * cpg]) + (addb ? addb[tid * cpg] : 0.0f);
+    __syncthreads();
+    // per-thread constants while the copies fly
+    const int g0 = c0 / cpg;
+    const int split = min(8, (g0 + 1) * cpg - c0);      // channels [0, split) of this thread are in group g0, the rest in g0+1
+    float gm[8], bt[8], sh[8];
+    {
+        const float4 a0 = *reinterpret_cast<const float4*>(gamma + c0), a1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+        gm[0] = a0.x; gm[1] = a0.y; gm[2] = a0.z; gm[3] = a0.w; gm[4] = a1.x; gm[5] = a1.y; gm[6] = a1.z; gm[7] = a1.w;
+        bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh[i] = (addb ? addb[c0 + i] : 0.0f) - Kg[i < split ? g0 : g0 + 1];
+    }
+    {   // wait for the slab
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(gn_smem_u32(mbar)) : "memory");
+        }
+    }
+    // ---- pass 1: shifted sums per channel -> two group partials per thread
+    float a1s[8], a2s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a1s[i] = 0.0f; a2s[i] = 0.0f; }
+    {
+        auto acc = [&](const Vec8<T>& tv) {
+            float f[8];
+            tv.unpack(f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = f[i] + sh[i]; a1s[i] += d; a2s[i] = fmaf(d, d, a2s[i]); }
+        };
+        int p = ph;
+        for (; p + PH < ms; p += 2 * PH) {
+            Vec8<T> t0, t1;
+            t0.load(slab + (size_t)p * C + c0);
+            t1.load(slab + (size_t)(p + PH) * C + c0);
+            acc(t0);
+            acc(t1);
+        }
+        for (; p < ms; p += PH) {
+            Vec8<T> t0;
+            t0.load(slab + (size_t)p * C + c0);
+            acc(t0);
+        }
+        for (; p + PH < my; p += 2 * PH) {               // streamed remainder (p >= spix)
+            Vec8<T> t0, t1;
+            t0.load(xg + (size_t)p * C + c0);
+            t1.load(xg + (size_t)(p + PH) * C + c0);
+            acc(t0);
+            acc(t1);
+        }
+        for (; p < my; p += PH) {
+            Vec8<T> t0;
+            t0.load(xg + (size_t)p * C + c0);
+            acc(t0);
+        }
+    }
+    {
+        float A1 = 0.0f, A2 = 0.0f, B1 = 0.0f, B2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < split) { A1 += a1s[i]; A2 += a2s[i]; }
+            else { B1 += a1s[i]; B2 += a2s[i]; }
+        }
+        red[ph * V + v] = make_float4(A1, A2, B1, B2);
+    }
+    __syncthreads();
+    {   // warp w reduces groups w, w + nwarps, ...: entries of the columns that overlap the group, all pixel phases
+        const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+        for (int g = warp; g < G; g += nwarps) {
+            const int vlo = (g * cpg) >> 3, vhi = ((g + 1) * cpg - 1) >> 3, nv = vhi - vlo + 1;
+            float t1 = 0.0f, t2 = 0.0f;
+            for (int e = lane; e < nv * PH; e += 32) {
+                const int vv = vlo + e % nv, pp = e / nv;
+                const float4 r = red[pp * V + vv];
+                const bool first = ((vv << 3) / cpg) == g;      // this group is the column's first (A) or second (B) group
+                t1 += first ? r.x : r.z;
+                t2 += first ? r.y : r.w;
+            }
+            t1 = warp_sum(t1);
+            t2 = warp_sum(t2);
+            if (lane == 0) part[g] = make_float2(t1, t2);
+        }
+    }
+    // ---- combine the S CTAs of the sample through distributed shared memory
+    if (S > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    if (tid < G) {
+        float t1 = 0.0f, t2 = 0.0f;
+        if (S > 1) {
+            const uint32_t local = gn_smem_u32(&part[tid]);
+            for (int r = 0; r < S; ++r) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+                float2 w;
+                asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(w.x), "=f"(w.y) : "r"(remote) : "memory");
+                t1 += w.x;
+                t2 += w.y;
+            }
+        } else {
+            t1 = part[tid].x;
+            t2 = part[tid].y;
+        }
+        const float inv_n = __fdividef(1.0f, (float)cpg * (float)HW);
+        const float m = t1 * inv_n;
+        const float var = fmaxf(t2 - t1 * m, 0.0f) * inv_n;
+        grp[tid] = make_float2(Kg[tid] + m, rsqrtf(var + eps));
+    }
+    if (S > 1) {     // also keeps every CTA's shared memory alive until its peers have read it
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    // ---- pass 2: normalise (+ SiLU) from shared memory
+    float sa[8], sb[8];
+    {
+        const int g1 = min(g0 + 1, G - 1);
+        const float2 sA = grp[g0], sB = grp[g1];
+        const float dA = Kg[g0] - sA.x, dB = Kg[g1] - sB.x;      // chan_add - mean = sh + (K_g - mean)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sa[i] = (i < split ? sA.y : sB.y) * gm[i];
+            sb[i] = bt[i] + (sh[i] + (i < split ? dA : dB)) * sa[i];
+            if (apply_silu == 2) { sa[i] *= 0.5f; sb[i] *= 0.5f; }
+        }
+    }
+    {
+        int p = ph;
+        for (; p + PH < ms; p += 2 * PH) {
+            Vec8<T> t0, t1;
+            t0.load(slab + (size_t)p * C + c0);
+            t1.load(slab + (size_t)(p + PH) * C + c0);
+            gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
+            gn_emit(t1, sa, sb, apply_silu, yg + (size_t)(p + PH) * C + c0);
+        }
+        for (; p < ms; p += PH) {
+            Vec8<T> t0;
+            t0.load(slab + (size_t)p * C + c0);
+            gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
+        }
+        for (; p + PH < my; p += 2 * PH) {
+            Vec8<T> t0, t1;
+            t0.load(xg + (size_t)p * C + c0);
+            t1.load(xg + (size_t)(p + PH) * C + c0);
+            gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
+            gn_emit(t1, sa, sb, apply_silu, yg + (size_t)(p + PH) * C + c0);
+        }
+        for (; p < my; p += PH) {
+            Vec8<T> t0;
+            t0.load(xg + (size_t)p * C + c0);
+            gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
+        }
+    }
+}
+
+struct GncPlan {
+    bool ok;
+    int V, PH, threads, S, npix, spix;
+    size_t smem;
+};
+
+static GncPlan gnc_plan(int B, int C, int HW, int G, size_t esize) {
+    GncPlan p{};
+    p.V = C >> 3;
+    const int cpg = C / G;
+    if (cpg < 8 || p.V > GNC_THREADS || C % 8 != 0) return p;
+    p.PH = GNC_THREADS / p.V;
+    if (p.PH > HW) p.PH = HW;
+    p.threads = p.V * p.PH;
+    const size_t pix_bytes = (size_t)C * esize;
+    const size_t sample = pix_bytes * HW;
+    if (sample > (size_t)24 * GNC_SLAB_BUDGET) return p;                    // at most 2/3 of a slab streamed from L2
+    int S = 1;
+    while (S < 8 && sample > (size_t)S * GNC_SLAB_BUDGET) S *= 2;           // fit the slabs in shared memory ...
+    while (S < 8 && (int64_t)B * S < num_sms() && HW / (S * 2) >= p.PH) S *= 2;   // ... and use the SMs
+    while (S > 1 && HW < S) S /= 2;
+    p.S = S;
+    p.npix = (HW + S - 1) / S;
+    p.spix = (int)(GNC_SLAB_BUDGET / pix_bytes);
+    if (p.spix > p.npix) p.spix = p.npix;
+    const size_t slab = (((size_t)p.spix * pix_bytes) + 127) & ~(size_t)127;
+    p.smem = slab + (size_t)p.PH * p.V * sizeof(float4) + 2 * GN_MAX_G * sizeof(float2) + GN_MAX_G * sizeof(float) + 16;
+    p.ok = true;
+    return p;
+}
+
+template <typename T>
+static int launch_cluster(const GncPlan& p, const T* x, const float* gamma, const float* beta, const float* chan_add,
+                          int64_t add_stride, T* y, int B, int C, int HW, int G, float eps, int silu, cudaStream_t s) {
+    DADD_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "dadd_groupnorm_fwd(NHWC)");
+    auto kern = gn_cluster_kernel<T>;
+    static bool configured = false;       // per template instance
+    if (!configured) {
+        if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024), "gn smem")) return 2;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.S, B, 1);
+    cfg.blockDim = dim3(p.threads, 1, 1);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, x, gamma, beta, chan_add, add_stride, y, HW, C, G, eps, silu, p.npix, p.spix, p.S);
+    if (e != cudaSuccess) return cuda_ok(e, "dadd_groupnorm_fwd(NHWC cluster) launch");
+    return launched("dadd_groupnorm_fwd(NHWC cluster)");
 }
 
 // ------------------------------------------------------------------------------------------------ NCHW
@@ -294,49 +616,35 @@ __global__ void __launch_bounds__(512) gn_nchw_kernel(const T* __restrict__ x, c
     }
 }
 
+static int64_t gn_workspace_bytes(int B, int C, int HW, int G) {
+    const GnPlan p = gn_plan(B, C, HW);
+    return (int64_t)B * p.chunks * G * sizeof(float2) + (int64_t)B * 2 * C * sizeof(float);
+}
+
 template <typename T>
 static int launch_nhwc(const T* x, const float* gamma, const float* beta, const float* chan_add, int64_t add_stride, T* y, int B, int C,
-                       int HW, int G, float eps, int silu, cudaStream_t s) {
-    const int V = C / 8;
-    DADD_REQUIRE(V <= 512, "dadd_groupnorm_fwd(NHWC)");
-    const int PH = 512 / V;
-    const int threads = V * PH;
-    // cluster size: largest power of two <= 8 dividing HW that keeps >= 8 pixels per CTA
-    static const int max_cluster = [] {
-        const char* e = getenv("DADD_GN_MAX_CLUSTER");
-        int v = e ? atoi(e) : 8;
-        return v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1)));
-    }();
-    int S = 1;
-    while (S < max_cluster && HW % (S * 2) == 0 && HW / (S * 2) >= 8) S *= 2;
-    const int npix = HW / S;
-    const bool cached = sizeof(T) == 2 && (npix + PH - 1) / PH <= GN_CACHE;
-    const size_t smem = ((size_t)2 * PH * C + C) * sizeof(float);
-    auto kern = gn_nhwc_kernel<T, false>;
-    if constexpr (sizeof(T) == 2) {
-        if (cached) kern = gn_nhwc_kernel<T, true>;
-    }
+                       int HW, int G, float eps, int silu, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+    DADD_REQUIRE(C / 8 <= 512, "dadd_groupnorm_fwd(NHWC)");
+    static const bool force_flat = [] { const char* e = getenv("DADD_GN_FLAT"); return e && atoi(e) != 0; }();
+    const GncPlan cp = gnc_plan(B, C, HW, G, sizeof(T));
+    if (cp.ok && !force_flat) return launch_cluster(cp, x, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, s);
+    DADD_REQUIRE(workspace != nullptr && workspace_bytes >= gn_workspace_bytes(B, C, HW, G), "dadd_groupnorm_fwd(NHWC)");
+    DADD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dadd_groupnorm_fwd(NHWC)");
+    const GnPlan p = gn_plan(B, C, HW);
+    float* coef = static_cast<float*>(workspace);                                   // [B][2][C], 16-byte aligned rows
+    float2* part = reinterpret_cast<float2*>(coef + (size_t)B * 2 * C);             // [B][chunks][G]
+    const size_t smem = (size_t)2 * p.PH * C * sizeof(float);
+    auto stats = gn_stats_nhwc_kernel<T>;
     if (smem > 48 * 1024) {
-        if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "gn smem")) return 2;
+        if (cuda_ok(cudaFuncSetAttribute(stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "gn smem")) return 2;
     }
-    if (S > 8) {
-        if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "gn cluster16")) return 2;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(S, B, 1);
-    cfg.blockDim = dim3(threads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = S;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, x, gamma, beta, chan_add, add_stride, y, HW, C, G, eps, silu, S);
-    if (e != cudaSuccess) return cuda_ok(e, "dadd_groupnorm_fwd(NHWC) launch");
-    return launched("dadd_groupnorm_fwd(NHWC)");
+    const dim3 grid(p.chunks, B, 1);
+    stats<<<grid, p.threads, smem, s>>>(x, chan_add, add_stride, part, HW, C, G, p.npx);
+    if (int rc = launched("dadd_groupnorm_fwd(NHWC stats)")) return rc;
+    gn_final_kernel<T><<<B, 256, 0, s>>>(part, x, gamma, beta, chan_add, add_stride, coef, p.chunks, HW, C, G, eps);
+    if (int rc = launched("dadd_groupnorm_fwd(NHWC final)")) return rc;
+    gn_apply_nhwc_kernel<T><<<grid, p.threads, 0, s>>>(x, coef, y, HW, C, silu, p.npx);
+    return launched("dadd_groupnorm_fwd(NHWC apply)");
 }
 
 template <typename T>
@@ -360,10 +668,15 @@ static int launch_nchw(const T* x, const float* gamma, const float* beta, const 
 
 using namespace daddk;
 
+extern "C" int64_t dadd_groupnorm_workspace_bytes(int B, int C, int HW, int G, int layout) {
+    if (layout != DADD_LAYOUT_NHWC || B <= 0 || C <= 0 || HW <= 0 || G <= 0 || C % 8 != 0) return 0;
+    return gn_workspace_bytes(B, C, HW, G);
+}
+
 extern "C" int dadd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* chan_add,
                                   int64_t chan_add_stride, void* y,
                                   int B, int C, int HW, int G, float eps, int apply_silu, int layout, int dtype,
-                                  void* stream) {
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
     DADD_REQUIRE(x && y && gamma && beta, "dadd_groupnorm_fwd");
     DADD_REQUIRE(B >= 0 && C > 0 && HW > 0 && G > 0 && G <= GN_MAX_G, "dadd_groupnorm_fwd");
     DADD_REQUIRE(C % G == 0 && C % 8 == 0, "dadd_groupnorm_fwd");
@@ -371,8 +684,12 @@ extern "C" int dadd_groupnorm_fwd(const void* x, const float* gamma, const float
     DADD_REQUIRE(layout == DADD_LAYOUT_NCHW || layout == DADD_LAYOUT_NHWC, "dadd_groupnorm_fwd");
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    // 16-bit outputs take SiLU as h + h * tanh(h) (one MUFU op per element; |error| <= 2^-11 |h|, below the output's own
+    // rounding for all but strongly negative pre-activations); DADD_SILU_EXACT=1 forces o / (1 + exp(-o)) everywhere.
+    static const bool silu_exact = [] { const char* e = getenv("DADD_SILU_EXACT"); return e && atoi(e) != 0; }();
+    if (apply_silu) apply_silu = (dtype != DADD_F32 && layout == DADD_LAYOUT_NHWC && !silu_exact) ? 2 : 1;
     if (layout == DADD_LAYOUT_NHWC)
-        DADD_DISPATCH_ANY(dtype, T, return launch_nhwc((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
+        DADD_DISPATCH_ANY(dtype, T, return launch_nhwc((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, workspace, workspace_bytes, s));
     DADD_DISPATCH_ANY(dtype, T, return launch_nchw((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
     return 1;
 }

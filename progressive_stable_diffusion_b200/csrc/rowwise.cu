@@ -8,59 +8,117 @@ namespace daddk {
 
 constexpr int LN_MAX_VEC = 8;  // 8 vectors x 8 elements x 32 lanes = C <= 2048
 
-// One warp per row, the row lives in registers: exact two-pass mean / variance in fp32.
-template <typename T>
-__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, T* __restrict__ y, int64_t rows,
-                                                        int C, float eps) {
+// (optional residual add +) LayerNorm, one warp per row, R rows per warp in flight, the rows packed in registers.
+//   s = x (+ y) rounded to T (written to sum_out when given);  out = LayerNorm(s) * gamma + beta.
+// Exact two-pass mean / variance in fp32.  NV = ceil(C / 256) 16-byte vectors per lane.  All loads of the R rows are
+// issued before the first reduction: R * C * sizeof(T) bytes in flight per warp (the kernel is latency-bound otherwise).
+template <typename T, int NV, int R, bool ADD>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const T* __restrict__ yadd, T* __restrict__ sum_out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        T* __restrict__ out, int64_t rows, int C, float eps) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (row0 >= rows) return;
     const int nvec = C >> 3;
-    const T* xr = x + row * C;
-    T* yr = y + row * C;
-    float f[LN_MAX_VEC][8];
-    float sum = 0.0f;
+    Vec8<T> vx[R][NV], vy[ADD ? R : 1][ADD ? NV : 1];
 #pragma unroll
-    for (int j = 0; j < LN_MAX_VEC; ++j) {
-        const int iv = lane + j * 32;
-        if (iv < nvec) {
-            Vec8<T> t;
-            t.load(xr + (iv << 3));
-            t.unpack(f[j]);
+    for (int r = 0; r < R; ++r) {
+        if (row0 + r < rows) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sum += f[j][i];
+            for (int j = 0; j < NV; ++j) {
+                const int iv = lane + j * 32;
+                if (iv < nvec) {
+                    vx[r][j].load(x + (row0 + r) * C + (iv << 3));
+                    if constexpr (ADD) vy[r][j].load(yadd + (row0 + r) * C + (iv << 3));
+                }
+            }
         }
     }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.0f;
+    const float inv_c = 1.0f / (float)C;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_VEC; ++j) {
-        const int iv = lane + j * 32;
-        if (iv < nvec) {
+    for (int r = 0; r < R; ++r) {
+        if (row0 + r >= rows) break;
+        float f[NV][8];
+        float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; sq += d * d; }
+        for (int j = 0; j < NV; ++j) {
+            const int iv = lane + j * 32;
+            if (iv < nvec) {
+                vx[r][j].unpack(f[j]);
+                if constexpr (ADD) {
+                    float g[8];
+                    vy[r][j].unpack(g);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[j][i] += g[i];
+                    Vec8<T> t;
+                    t.pack(f[j]);
+                    if (sum_out) t.store(sum_out + (row0 + r) * C + (iv << 3));
+                    t.unpack(f[j]);                       // LayerNorm sees the rounded sum, like the unfused graph
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) { s0 += f[j][i]; s1 += f[j][i + 1]; }
+            }
+        }
+        const float mean = warp_sum(s0 + s1) * inv_c;
+        float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int iv = lane + j * 32;
+            if (iv < nvec) {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    const float d0 = f[j][i] - mean, d1 = f[j][i + 1] - mean;
+                    q0 = fmaf(d0, d0, q0);
+                    q1 = fmaf(d1, d1, q1);
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q0 + q1) * inv_c + eps);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int iv = lane + j * 32;
+            if (iv < nvec) {
+                const float4 g0 = *reinterpret_cast<const float4*>(gamma + (iv << 3));
+                const float4 g1 = *reinterpret_cast<const float4*>(gamma + (iv << 3) + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(beta + (iv << 3));
+                const float4 b1 = *reinterpret_cast<const float4*>(beta + (iv << 3) + 4);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = (f[j][i] - mean) * rstd * g[i] + bb[i];
+                Vec8<T> t;
+                t.pack(o);
+                t.store(out + (row0 + r) * C + (iv << 3));
+            }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-#pragma unroll
-    for (int j = 0; j < LN_MAX_VEC; ++j) {
-        const int iv = lane + j * 32;
-        if (iv < nvec) {
-            const float4 g0 = *reinterpret_cast<const float4*>(gamma + (iv << 3));
-            const float4 g1 = *reinterpret_cast<const float4*>(gamma + (iv << 3) + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(beta + (iv << 3));
-            const float4 b1 = *reinterpret_cast<const float4*>(beta + (iv << 3) + 4);
-            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (f[j][i] - mean) * rstd * g[i] + bb[i];
-            Vec8<T> t;
-            t.pack(o);
-            t.store(yr + (iv << 3));
-        }
+}
+
+template <typename T, bool ADD>
+static int launch_layernorm(const T* x, const T* yadd, T* sum_out, const float* gamma, const float* beta, T* out, int64_t rows,
+                            int C, float eps, cudaStream_t s) {
+    const int nv = (C / 8 + 31) / 32;
+    const int wpb = 8;
+#define DADD_LN(NVV, RR)                                                                                                  \
+    do {                                                                                                                  \
+        const int64_t per_block = (int64_t)wpb * RR;                                                                      \
+        layernorm_kernel<T, NVV, RR, ADD><<<(unsigned)((rows + per_block - 1) / per_block), wpb * 32, 0, s>>>(            \
+            x, yadd, sum_out, gamma, beta, out, rows, C, eps);                                                            \
+        return launched("dadd_layernorm_fwd");                                                                            \
+    } while (0)
+    if constexpr (sizeof(T) == 2) {
+        if (nv <= 1) DADD_LN(1, 4);
+        if (nv == 2) DADD_LN(2, 4);
+        if (nv == 3) DADD_LN(3, 2);
+        if (nv <= 5) DADD_LN(5, 1);
+        DADD_LN(8, 1);
+    } else {
+        if (nv <= 1) DADD_LN(1, 2);
+        if (nv <= 3) DADD_LN(3, 1);
+        DADD_LN(8, 1);
     }
+#undef DADD_LN
 }
 
 __device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
@@ -182,10 +240,20 @@ int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
     DADD_REQUIRE(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 256, "dadd_layernorm_fwd");
     DADD_REQUIRE(dtype_ok(dtype), "dadd_layernorm_fwd");
     if (rows == 0) return 0;
-    const int wpb = 8;
-    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    DADD_DISPATCH_ANY(dtype, T, (layernorm_kernel<T><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)y, rows, C, eps)));
-    return launched("dadd_layernorm_fwd");
+    DADD_DISPATCH_ANY(dtype, T, return (launch_layernorm<T, false>((const T*)x, nullptr, nullptr, gamma, beta, (T*)y, rows, C, eps,
+                                                                   (cudaStream_t)stream)));
+    return 1;
+}
+
+int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out, const float* gamma, const float* beta, void* y,
+                           int64_t rows, int C, float eps, int dtype, void* stream) {
+    DADD_REQUIRE(x && r && y && gamma && beta && rows >= 0, "dadd_add_layernorm_fwd");
+    DADD_REQUIRE(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 256, "dadd_add_layernorm_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_add_layernorm_fwd");
+    if (rows == 0) return 0;
+    DADD_DISPATCH_ANY(dtype, T, return (launch_layernorm<T, true>((const T*)x, (const T*)r, (T*)sum_out, gamma, beta, (T*)y, rows, C,
+                                                                  eps, (cudaStream_t)stream)));
+    return 1;
 }
 
 int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream) {

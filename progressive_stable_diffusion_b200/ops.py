@@ -99,9 +99,14 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, num_gro
         assert chan_add.dtype == torch.float32 and chan_add.shape == (b, c) and chan_add.stride(1) == 1
     y = torch.empty_like(x) if out is None else out
     assert y.stride() == x.stride()
-    _lib.check(_lib.load().dadd_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(chan_add),
-                                              0 if chan_add is None else chan_add.stride(0), y.data_ptr(), b, c, h * w, num_groups, eps, int(silu), layout, _dt(x),
-                                              _stream()), "dadd_groupnorm_fwd")
+    lib = _lib.load()
+    ws, ws_bytes = None, 0
+    if layout == NHWC:      # the two-pass NHWC kernels keep their chunk partials in a caller-owned scratch buffer
+        ws_bytes = int(lib.dadd_groupnorm_workspace_bytes(b, c, h * w, num_groups, layout))
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.dadd_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(chan_add),
+                                      0 if chan_add is None else chan_add.stride(0), y.data_ptr(), b, c, h * w, num_groups, eps,
+                                      int(silu), layout, _dt(x), _ptr(ws), ws_bytes, _stream()), "dadd_groupnorm_fwd")
     return y
 
 
@@ -112,6 +117,46 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     y = torch.empty_like(x)
     _lib.check(_lib.load().dadd_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
                                               x.numel() // c, c, eps, _dt(x), _stream()), "dadd_layernorm_fwd")
+    return y
+
+
+def add_layer_norm(x: torch.Tensor, r: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                   want_sum: bool = True):
+    """``s = x + r`` (rounded to the tensor dtype) and ``LayerNorm(s)`` in one pass; returns ``(s or None, norm)``."""
+    _cuda(x, r, gamma, beta)
+    assert x.is_contiguous() and r.is_contiguous() and x.shape == r.shape and x.dtype == r.dtype
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    c = x.shape[-1]
+    s = torch.empty_like(x) if want_sum else None
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().dadd_add_layernorm_fwd(x.data_ptr(), r.data_ptr(), _ptr(s), gamma.data_ptr(), beta.data_ptr(),
+                                                  y.data_ptr(), x.numel() // c, c, eps, _dt(x), _stream()),
+               "dadd_add_layernorm_fwd")
+    return s, y
+
+
+def bias_residual(a: torch.Tensor, res: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``a (+ res) (+ bias[c])`` with the channel dimension innermost in memory: ``a`` is either a channels_last 4-D
+    activation ``(B, C, H, W)`` or a contiguous ``(..., C)`` token matrix; ``res`` must share its layout; bias is fp32."""
+    _cuda(a, res, bias)
+    assert res is not None or bias is not None
+    if a.dim() == 4 and not a.is_contiguous():
+        assert a.is_contiguous(memory_format=torch.channels_last)
+        c = a.shape[1]
+    else:
+        assert a.is_contiguous()
+        c = a.shape[-1] if a.dim() != 4 else a.shape[1] * a.shape[2] * a.shape[3] // max(1, a.shape[2] * a.shape[3])
+        if a.dim() == 4:        # contiguous NCHW only describes channel-innermost memory when H*W == 1
+            assert a.shape[2] * a.shape[3] == 1 or bias is None
+    if res is not None:
+        assert res.shape == a.shape and res.stride() == a.stride() and res.dtype == a.dtype
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == c and bias.is_contiguous()
+    y = torch.empty_like(a) if out is None else out
+    assert y.stride() == a.stride() and y.dtype == a.dtype
+    _lib.check(_lib.load().dadd_bias_residual_fwd(a.data_ptr(), _ptr(res), _ptr(bias), y.data_ptr(), a.numel() // c, c,
+                                                  _dt(a), _stream()), "dadd_bias_residual_fwd")
     return y
 
 

@@ -9,8 +9,11 @@ is kept.  Execution is B200-first:
 
 * activations are bf16 **channels-last** end to end: convolutions hit cuDNN's NHWC tensor-core kernels (off-path by the
   north-star), the Transformer2D entry/exit permutes are free views and the 1x1 ``proj_in/out`` are plain GEMMs;
-* every GroupNorm(+SiLU) is one ``dadd_groupnorm_fwd`` launch, with the resnet time-embedding add folded into ``norm2``;
-* LayerNorm and GEGLU are single fused kernels; self/cross attention are the processors' fused kernels;
+* every GroupNorm(+SiLU) is one ``dadd_groupnorm_fwd`` call, with the resnet time-embedding add folded into ``norm2``;
+* no convolution adds its own bias (PyTorch would launch a broadcasting add per conv): conv1's bias rides on the
+  time-embedding row, conv2's on the fused residual add (``dadd_bias_residual_fwd``) or the shortcut GEMM's epilogue;
+* LayerNorm is fused with the residual add that feeds it (``dadd_add_layernorm_fwd``), GEGLU is one kernel;
+  self/cross attention are the processors' fused kernels;
 * the 22 ``time_emb_proj`` matrices are one stacked fp32 GEMM per forward (or one per sampling call, see
   ``precompute_time_terms``), and nothing in ``forward`` synchronises, so a whole step can be captured in a CUDA graph.
 """
@@ -32,10 +35,23 @@ CL = torch.channels_last
 
 
 # ----------------------------------------------------------------------------------------------- leaf helpers
+def _conv_nobias(mod: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """cuDNN convolution without its bias: PyTorch adds a conv bias as a separate (slow, broadcasting) elementwise
+    kernel, so callers fold it into the kernel that consumes the result instead."""
+    return F.conv2d(x, wcache.conv_filter(mod, "w", mod.weight, compute_dtype()), None, mod.stride, mod.padding)
+
+
+def _bias32(mod, tag: str = "b32") -> Optional[torch.Tensor]:
+    return None if mod.bias is None else wcache.cast(mod, tag, mod.bias, torch.float32)
+
+
 def _conv(mod: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    w = wcache.conv_filter(mod, "w", mod.weight, compute_dtype())
-    b = None if mod.bias is None else wcache.cast(mod, "b", mod.bias, compute_dtype())
-    return F.conv2d(x, w, b, mod.stride, mod.padding)
+    y = _conv_nobias(mod, x)
+    if mod.bias is None:
+        return y
+    if mod.out_channels % 8 == 0:
+        return ops.bias_residual(y, None, _bias32(mod), out=y)      # one vectorised in-place pass
+    return y + wcache.cast(mod, "b", mod.bias, compute_dtype()).view(1, -1, 1, 1)
 
 
 def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
@@ -44,10 +60,28 @@ def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, w, b)
 
 
-def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor) -> torch.Tensor:
+def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor, extra_bias: Optional[nn.Module] = None) -> torch.Tensor:
+    """1x1 convolution as a GEMM on channels-last tokens (bias in the GEMM epilogue).  ``extra_bias``: a module whose bias
+    is added on top (a resnet's conv2 bias rides on its shortcut GEMM)."""
     w = wcache.get(mod, "w2d", (mod.weight,), lambda: mod.weight.detach().to(compute_dtype()).reshape(mod.out_channels, -1).contiguous())
-    b = wcache.cast(mod, "b", mod.bias, compute_dtype())
+    if extra_bias is None:
+        b = wcache.cast(mod, "b", mod.bias, compute_dtype())
+    else:
+        b = wcache.get(mod, "b+", (mod.bias, extra_bias.bias),
+                       lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).to(compute_dtype()).contiguous())
     return F.linear(tokens, w, b)
+
+
+def _tokens(x: torch.Tensor) -> torch.Tensor:
+    """(B, C, H, W) channels-last -> (B, H*W, C) view."""
+    b, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+
+
+def _image(t: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """(B, H*W, C) -> (B, C, H, W) channels-last view."""
+    b, _, c = t.shape
+    return t.view(b, h, w, c).permute(0, 3, 1, 2)
 
 
 def _gn(mod: nn.GroupNorm, x: torch.Tensor, silu: bool, chan_add: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -58,6 +92,12 @@ def _gn(mod: nn.GroupNorm, x: torch.Tensor, silu: bool, chan_add: Optional[torch
 def _ln(mod: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
     return ops.layer_norm(x, wcache.cast(mod, "w", mod.weight, torch.float32), wcache.cast(mod, "b", mod.bias, torch.float32),
                           mod.eps)
+
+
+def _add_ln(mod: nn.LayerNorm, x: torch.Tensor, r: torch.Tensor):
+    """(x + r, LayerNorm(x + r)) in one kernel."""
+    return ops.add_layer_norm(x, r, wcache.cast(mod, "w", mod.weight, torch.float32),
+                              wcache.cast(mod, "b", mod.bias, torch.float32), mod.eps)
 
 
 # ----------------------------------------------------------------------------------------------- modules
@@ -127,9 +167,11 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
-        x = x + self.attn1(_ln(self.norm1, x))
-        x = x + self.attn2(_ln(self.norm2, x), encoder_hidden_states=ehs)
-        return x + self.ff(_ln(self.norm3, x))
+        # hidden = attn(norm(hidden)) + hidden, three times; each residual add is fused with the
+        # LayerNorm that follows it, the last one is a plain vectorised add
+        x, n = _add_ln(self.norm2, x, self.attn1(_ln(self.norm1, x)))
+        x, n = _add_ln(self.norm3, x, self.attn2(n, encoder_hidden_states=ehs))
+        return ops.bias_residual(self.ff(n), x)
 
 
 class Transformer2DModel(nn.Module):
@@ -144,12 +186,12 @@ class Transformer2DModel(nn.Module):
 
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
         b, c, h, w = x.shape
-        t = _gn(self.norm, x, silu=False).permute(0, 2, 3, 1).reshape(b, h * w, c)      # free view (channels-last)
+        t = _tokens(_gn(self.norm, x, silu=False))                  # free view (channels-last)
         t = _conv1x1_as_linear(self.proj_in, t)
         for blk in self.transformer_blocks:
             t = blk(t, ehs)
         t = _conv1x1_as_linear(self.proj_out, t)
-        return t.view(b, h, w, c).permute(0, 3, 1, 2) + x
+        return _image(ops.bias_residual(t, _tokens(x)), h, w)
 
 
 class ResnetBlock2D(nn.Module):
@@ -164,12 +206,18 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x: torch.Tensor, temb_term: Optional[torch.Tensor]) -> torch.Tensor:
-        """``temb_term`` = time_emb_proj(silu(emb)) as fp32 (B, cout): folded into norm2's input by the GN kernel."""
-        h = _conv(self.conv1, _gn(self.norm1, x, silu=True))
-        h = _conv(self.conv2, _gn(self.norm2, h, silu=True, chan_add=temb_term))
-        if self.conv_shortcut is not None:
-            x = _conv(self.conv_shortcut, x)
-        return x + h
+        """``temb_term`` = time_emb_proj(silu(emb)) + conv1.bias as fp32 (B, cout) (``UNet2DConditionModel.time_terms``):
+        folded into norm2's input by the GN kernel.  No convolution adds its own bias: conv1's rides on ``temb_term``,
+        conv2's on the residual add (or on the shortcut GEMM's epilogue)."""
+        h = _conv_nobias(self.conv1, _gn(self.norm1, x, silu=True))
+        if temb_term is None:                                       # VAE resnets: only conv1's bias, one row for all samples
+            temb_term = _bias32(self.conv1).view(1, -1).expand(x.shape[0], -1)
+        h = _conv_nobias(self.conv2, _gn(self.norm2, h, silu=True, chan_add=temb_term))
+        if self.conv_shortcut is None:
+            return ops.bias_residual(h, x, _bias32(self.conv2), out=h)
+        b, _, hh, ww = x.shape
+        sc = _image(_conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2), hh, ww)
+        return ops.bias_residual(h, sc, out=h)
 
 
 class Downsample2D(nn.Module):
@@ -285,7 +333,8 @@ class UNet2DConditionModel(nn.Module):
 
     def time_terms(self, timesteps: torch.Tensor) -> torch.Tensor:
         """(T, sum C_out) fp32: sinusoid -> time_embedding MLP -> SiLU -> all 22 ``time_emb_proj`` as one stacked GEMM
-        (SURVEY.md A.2 step 1, A.3).  Row t is what every resnet adds before norm2 at that timestep."""
+        (SURVEY.md A.2 step 1, A.3), plus each resnet's ``conv1.bias``.  Row t is what every resnet adds to the bias-free
+        conv1 output before norm2 at that timestep."""
         half = self.config.block_out_channels[0] // 2
         dev = timesteps.device
         freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=dev) / half)
@@ -297,9 +346,11 @@ class UNet2DConditionModel(nn.Module):
         emb = F.linear(F.silu(emb), wcache.cast(te.linear_2, "w", te.linear_2.weight, f32), wcache.cast(te.linear_2, "b", te.linear_2.bias, f32))
         res = self._resnets()
         wsrc = tuple(r.time_emb_proj.weight for r in res)
-        bsrc = tuple(r.time_emb_proj.bias for r in res)
+        bsrc = tuple(r.time_emb_proj.bias for r in res) + tuple(r.conv1.bias for r in res)
         w = wcache.get(self, "temb_w", wsrc, lambda: torch.cat([p.detach().to(f32) for p in wsrc], 0).contiguous())
-        b = wcache.get(self, "temb_b", bsrc, lambda: torch.cat([p.detach().to(f32) for p in bsrc], 0).contiguous())
+        # conv1's bias is a per-channel constant added right before the time term: it rides on the same row
+        b = wcache.get(self, "temb_b", bsrc, lambda: torch.cat([r.time_emb_proj.bias.detach().to(f32) + r.conv1.bias.detach().to(f32)
+                                                                for r in res], 0).contiguous())
         return F.linear(F.silu(emb), w, b)
 
     def _split_terms(self, terms: torch.Tensor) -> Dict[int, torch.Tensor]:

@@ -134,7 +134,70 @@ def test_groupnorm_expanded_chan_add_row():
     assert (y.float().cpu() - ref).abs().max().item() < 0.04
 
 
+@pytest.mark.parametrize("b,c,hw", [(26, 320, 32), (13, 128, 128), (5, 960, 32), (2, 2560, 4), (1, 64, 200)])
+def test_groupnorm_nhwc_many_chunks_and_reproducible(b, c, hw):
+    """Shapes whose samples split into many pixel chunks (incl. > 16: the separate finalise pass, and ragged last chunks);
+    the two-pass kernels use no atomics, so two runs agree bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(b * c + hw)
+    x = (torch.randn(b, c, hw, hw, generator=g) * 2 - 1.3).to(torch.bfloat16)
+    gamma, beta = 1 + 0.2 * torch.randn(c, generator=g), 0.2 * torch.randn(c, generator=g)
+    add = torch.randn(b, c, generator=g)
+    ref = F.silu(F.group_norm(x.float() + add[:, :, None, None], 32, gamma, beta, 1e-5))
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    y1 = ops.group_norm(xd, gamma.to(DEV), beta.to(DEV), 32, 1e-5, True, add.to(DEV))
+    y2 = ops.group_norm(xd, gamma.to(DEV), beta.to(DEV), 32, 1e-5, True, add.to(DEV))
+    assert torch.equal(y1, y2)
+    assert (y1.float().cpu() - ref).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm / GEGLU
+@pytest.mark.parametrize("rows", [1, 7, 1024 * 3 + 5])
+@pytest.mark.parametrize("c", [320, 640, 1280, 768, 2048, 8])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_add_layernorm(rows, c, dtype):
+    """Residual add fused with the LayerNorm that consumes it: the sum is rounded to the tensor dtype first (what the
+    unfused graph feeds LayerNorm), ragged row counts exercise the rows-per-warp tail."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(c + rows)
+    x = (torch.randn(rows, c, generator=g) * 2 + 0.5).to(dtype)
+    r = torch.randn(rows, c, generator=g).to(dtype)
+    gamma, beta = 1 + 0.1 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    s_ref = (x.float() + r.float()).to(dtype)
+    ref = F.layer_norm(s_ref.float(), (c,), gamma, beta, 1e-5)
+    s, y = ops.add_layer_norm(x.to(DEV), r.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5)
+    assert torch.equal(s.cpu(), s_ref)
+    tol = {torch.bfloat16: 2.0 ** -7 * ref.abs().max().item(), torch.float16: 2.0 ** -10 * ref.abs().max().item(),
+           torch.float32: 3e-5}[dtype]
+    assert (y.float().cpu() - ref).abs().max().item() <= tol
+    _, y2 = ops.add_layer_norm(x.to(DEV), r.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5, want_sum=False)
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("shape", [(3, 320, 32, 32), (2, 1280, 4, 4), (26, 64, 640), (1, 1, 8), (5, 1031, 24)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_bias_residual(shape, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(sum(shape))
+    a = torch.randn(*shape, generator=g).to(dtype)
+    r = torch.randn(*shape, generator=g).to(dtype)
+    c = shape[1] if len(shape) == 4 else shape[-1]
+    bias = torch.randn(c, generator=g)
+    bview = bias.view(1, -1, 1, 1) if len(shape) == 4 else bias
+    ad, rd = a.to(DEV), r.to(DEV)
+    if len(shape) == 4:
+        ad, rd = ad.contiguous(memory_format=torch.channels_last), rd.contiguous(memory_format=torch.channels_last)
+    for use_r, use_b in ((True, True), (True, False), (False, True)):
+        ref = (a.float() + (r.float() if use_r else 0) + (bview if use_b else 0)).to(dtype)
+        y = ops.bias_residual(ad, rd if use_r else None, bias.to(DEV) if use_b else None)
+        assert y.stride() == ad.stride()
+        assert torch.equal(y.cpu(), ref), (use_r, use_b)
+    y = ops.bias_residual(ad.clone(), rd, bias.to(DEV), out=None)
+    inplace = ad.clone()
+    ops.bias_residual(inplace, rd, bias.to(DEV), out=inplace)
+    assert torch.equal(inplace, y)
+
+
 @pytest.mark.parametrize("c", [320, 640, 1280, 768])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 def test_layernorm(c, dtype):
