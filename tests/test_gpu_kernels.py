@@ -229,12 +229,12 @@ SELF_SHAPES = [(1024, 40, 2), (256, 80, 2), (64, 160, 3), (16, 160, 2), (100, 40
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
-@pytest.mark.parametrize("impl", ["mma", "tc"])
+@pytest.mark.parametrize("impl", ["mma", "tc", "tc1"])
 @pytest.mark.parametrize("n,d,b", SELF_SHAPES)
 def test_self_attention_core(n, d, b, impl, dtype):
     """Both self-attention kernels (warp-level mma.sync; tcgen05/TMEM/TMA) against fp32 SDPA on the same 16-bit inputs."""
     ops = _ops()
-    if impl == "tc" and n < 128:
+    if impl in ("tc", "tc1") and n < 128:
         pytest.skip("the tcgen05 kernel takes N >= 128 (shorter sequences are one mma.sync tile)")
     h = 8
     g = torch.Generator().manual_seed(n + d)
@@ -247,6 +247,29 @@ def test_self_attention_core(n, d, b, impl, dtype):
     torch.cuda.synchronize()
     tol = 1.5e-2 if dtype == torch.bfloat16 else 3e-3
     assert rel_err(o, ref) <= tol, rel_err(o, ref)
+
+
+@pytest.mark.parametrize("n,d,b", [(1024, 40, 26), (640, 80, 20), (256, 64, 40)])
+def test_self_attention_persistent_many_items_and_growing_maxima(n, d, b):
+    """More work items than SMs (every persistent CTA walks several), and scores whose row maxima keep growing along the
+    key axis by far more than 2^8 so the lazy O-rescale path runs on most key tiles."""
+    ops = _ops()
+    h = 8
+    c = h * d
+    g = torch.Generator().manual_seed(n * d + b)
+    qkv = torch.randn(b, n, 3 * c, generator=g)
+    ramp = torch.linspace(0.0, 6.0, n)[None, :, None]                  # |k| grows with the key index
+    qkv[..., c:2 * c] *= (0.3 + ramp)
+    qkv[..., :c] *= 1.5
+    qkv = qkv.to(torch.bfloat16)
+    q, k, v = (qkv[..., i * c:(i + 1) * c].float().view(b, n, h, d).transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+    qd = qkv.to(DEV)
+    o = ops.self_attention(qd[..., :c], qd[..., c:2 * c], qd[..., 2 * c:], h, impl="tc")
+    o1 = ops.self_attention(qd[..., :c], qd[..., c:2 * c], qd[..., 2 * c:], h, impl="tc1")
+    torch.cuda.synchronize()
+    assert rel_err(o, ref) <= 1.5e-2, rel_err(o, ref)
+    assert rel_err(o1, ref) <= 1.5e-2, rel_err(o1, ref)
 
 
 def test_self_attention_dispatch_uses_both_kernels():
