@@ -3,7 +3,8 @@
 //   z = g_a softmax(Q Ka^T/sqrt d) Va + g_d softmax(Q Kd^T/sqrt d) Vd (+ lambda softmax(Q Kx^T/sqrt d) Vx)
 // and OrdinalIPAttnProcessor2_0.__call__ (src/models/attention_processor_base.py:96-118) as one 32-token segment.
 //
-// The whole K/V of one (sample, head) is <= 64 x 160 16-bit elements and lives in shared memory; each warp owns 16
+// The whole K/V of one (sample, head) is <= 64 x 160 16-bit elements and lives in shared memory (pulled in with cp.async:
+// one global round trip for Q, K and V; V stays row-major and is read through ldmatrix.trans); each warp owns 16
 // query rows: S = Q K_cat^T (one pass, all segments), an independent softmax per 16-token segment in registers, the
 // gate of the segment folded into the normalisation (invariant I11: sum_s g_s P_s V_s = [g_s P_s]_s V_cat), O = P V_cat.
 // No score tensor is materialised; HBM traffic is Q in + O out (+ the tiny K/V), which is the roofline of this op
@@ -13,19 +14,31 @@
 
 namespace daddk {
 
+// 16-byte global -> shared copy that does not pass through registers; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+
+// B fragment (16 keys x 8 columns) of a row-major [key][column] tile: ldmatrix with transpose
+__device__ __forceinline__ void load_b_frag_trans(uint32_t& b0, uint32_t& b1, const void* row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(b0), "=r"(b1)
+                 : "r"((uint32_t)__cvta_generic_to_shared(row_ptr)));
+}
+
 template <typename T, int DK>
 __global__ void __launch_bounds__(128) cross_attn_kernel(const T* __restrict__ q, int64_t q_stride,
                                                          const T* __restrict__ k_cat, const T* __restrict__ v_cat,
                                                          T* __restrict__ o, int64_t o_stride, int H, int N, int d,
                                                          int seg_len, int n_seg, const float* __restrict__ gates,
                                                          float scale_log2e) {
-    constexpr int QS = DK + 8;          // smem row stride (elements): conflict-free 32-bit fragment loads
+    constexpr int QS = DK + 8;          // smem row stride (elements): conflict-free 32-bit fragment loads and ldmatrix rows
     constexpr int LMAX = 64;
-    constexpr int VS = LMAX + 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Qs = reinterpret_cast<T*>(smem_raw);   // [64][QS]
     T* Ks = Qs + 64 * QS;                      // [LMAX][QS]
-    T* Vt = Ks + LMAX * QS;                    // [DK][VS]  (transposed V)
+    T* Vs = Ks + LMAX * QS;                    // [LMAX][QS]  (row-major; PV reads it through ldmatrix.trans)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -38,27 +51,20 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const T* __restrict__ q
     const T* kb = k_cat + ((int64_t)(b * H + h) * L) * d;
     const T* vb = v_cat + ((int64_t)(b * H + h) * L) * d;
 
+    // all copies are issued back to back (cp.async), one wait: a single global round trip for Q, K and V
     constexpr int DKV = DK >> 3;
     for (int i = tid; i < 64 * DKV; i += 128) {
         const int r = i / DKV, c = i % DKV;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (c < dv && row0 + r < N) val = *reinterpret_cast<const uint4*>(qb + (int64_t)r * q_stride + c * 8);
-        *reinterpret_cast<uint4*>(Qs + r * QS + c * 8) = val;
+        const bool ok = c < dv && row0 + r < N;
+        cp_async16(Qs + r * QS + c * 8, ok ? qb + (int64_t)r * q_stride + c * 8 : q, ok ? 16 : 0);
     }
-    for (int i = tid; i < LMAX * DKV; i += 128) {
+    for (int i = tid; i < L * DKV; i += 128) {
         const int r = i / DKV, c = i % DKV;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (c < dv && r < L) val = *reinterpret_cast<const uint4*>(kb + (int64_t)r * d + c * 8);
-        *reinterpret_cast<uint4*>(Ks + r * QS + c * 8) = val;
+        const bool ok = c < dv;
+        cp_async16(Ks + r * QS + c * 8, ok ? kb + (int64_t)r * d + c * 8 : k_cat, ok ? 16 : 0);
+        cp_async16(Vs + r * QS + c * 8, ok ? vb + (int64_t)r * d + c * 8 : v_cat, ok ? 16 : 0);
     }
-    for (int i = tid; i < LMAX * dv; i += 128) {
-        const int r = i / dv, c = i % dv;      // token r, chunk c
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (r < L) val = *reinterpret_cast<const uint4*>(vb + (int64_t)r * d + c * 8);
-        const T* e = reinterpret_cast<const T*>(&val);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) Vt[(c * 8 + j) * VS + r] = e[j];
-    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- S = Q K^T for this warp's 16 rows, all L tokens -----------------------------------------------------
@@ -131,8 +137,8 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const T* __restrict__ q
 #pragma unroll
             for (int nd = 0; nd < DK / 8; ++nd) {
                 if (nd < dv) {
-                    uint32_t b0, b1;
-                    load_b_frag(b0, b1, Vt + (nd * 8) * VS, VS, kk * 16, g, t);
+                    uint32_t b0, b1;      // lanes 0-15 address the 16 key rows of this k-step, 8 columns wide
+                    load_b_frag_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * QS + nd * 8);
                     mma_16816<T>(acc[nd], a, b0, b1);
                 }
             }
@@ -161,7 +167,7 @@ template <typename T, int DK>
 static int launch_cross(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
                         int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg, const float* gates,
                         float scale, cudaStream_t s) {
-    const size_t smem = ((size_t)64 * (DK + 8) * 2 + (size_t)DK * 72) * sizeof(T);
+    const size_t smem = (size_t)3 * 64 * (DK + 8) * sizeof(T);
     auto kern = cross_attn_kernel<T, DK>;
     if (smem > 48 * 1024) {
         if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cross_attn smem"))

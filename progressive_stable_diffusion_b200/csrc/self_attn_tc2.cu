@@ -235,13 +235,16 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
             DADD_TRACE_EVENT(2, s, 2);
             issue_pv(0, s);
             DADD_TRACE_EVENT(2, s, 3);
+            // at the end of an item group 0 is busy with its epilogue, so group 1's P arrives first: serve it first
+            const bool item_end = (s + 1) % (uint32_t)nkv == 0;
+            if (item_end) issue_pv(1, s);
             if (s + 2 < steps) {
                 mbar_wait(&bars->s_read[0], (s + 1) & 1);
                 DADD_TRACE_EVENT(2, s, 4);
                 issue_qk(0, s + 2);
             }
             DADD_TRACE_EVENT(2, s, 5);
-            issue_pv(1, s);
+            if (!item_end) issue_pv(1, s);
             DADD_TRACE_EVENT(2, s, 6);
         }
     } else if (warp < 8) {
@@ -389,16 +392,22 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
             unsigned char* stage = sO + q * NP * Q_PANEL + wrow * 128;
             const int chunks = (d + 7) >> 3;
 #pragma unroll 1
-            for (int c = 0; c < chunks; ++c) {
-                uint32_t r[8];
-                tmem_ld8(tO + c * 8, r);
+            for (int c0 = 0; c0 < chunks; c0 += 4) {                 // 32 columns per round trip to TMEM
+                uint32_t r[32];
+                tmem_ld32(tO + c0 * 8, r);
                 tmem_wait_ld();
-                uint4 out;
-                out.x = pack2<T>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-                out.y = pack2<T>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-                out.z = pack2<T>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-                out.w = pack2<T>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-                *reinterpret_cast<uint4*>(stage + (c >> 3) * Q_PANEL + (((c & 7) ^ (wrow & 7)) << 4)) = out;   // 128-byte swizzle
+#pragma unroll
+                for (int cc4 = 0; cc4 < 4; ++cc4) {
+                    const int c = c0 + cc4;
+                    if (c < chunks) {
+                        uint4 out;
+                        out.x = pack2<T>(__uint_as_float(r[cc4 * 8 + 0]) * inv, __uint_as_float(r[cc4 * 8 + 1]) * inv);
+                        out.y = pack2<T>(__uint_as_float(r[cc4 * 8 + 2]) * inv, __uint_as_float(r[cc4 * 8 + 3]) * inv);
+                        out.z = pack2<T>(__uint_as_float(r[cc4 * 8 + 4]) * inv, __uint_as_float(r[cc4 * 8 + 5]) * inv);
+                        out.w = pack2<T>(__uint_as_float(r[cc4 * 8 + 6]) * inv, __uint_as_float(r[cc4 * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(stage + (c >> 3) * Q_PANEL + (((c & 7) ^ (wrow & 7)) << 4)) = out;   // 128-byte swizzle
+                    }
+                }
             }
             fence_before();      // the O reads above are ordered before the next item's first P arrive (-> PV overwrites O)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

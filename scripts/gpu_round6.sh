@@ -1,0 +1,7 @@
+mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
+timeout 900 python -m pytest tests -m gpu -q -x --timeout=900 -p no:cacheprovider -k "cross or model or smoke" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/summary.txt
+timeout 300 python scripts/kbench.py --kernel cross > gpurun_out/kb_cross.log 2>&1
+for P in 2 8; do
+timeout 600 python scripts/profile_step.py --patients $P > gpurun_out/profile_p$P.log 2>&1; echo "profile P=$P rc=$?" >> gpurun_out/summary.txt
+done
+cat gpurun_out/summary.txt; tail -4 gpurun_out/pytest_gpu.log; cat gpurun_out/kb_cross.log; tail -2 gpurun_out/profile_p2.log gpurun_out/profile_p8.log
