@@ -21,7 +21,6 @@ is kept.  Execution is B200-first:
 from __future__ import annotations
 
 import math
-import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
@@ -153,25 +152,10 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
-    # The (rows, 8C) GEGLU input is the largest activation of the UNet (136 MB at 26 x 1024 x 320): above this size the
-    # batch is processed in slices so that proj -> GEGLU -> out stays inside the 126 MB L2 instead of round-tripping HBM.
-    L2_SLICE_BYTES = int(os.environ.get("DADD_FF_SLICE_MB", "48")) << 20      # 0 disables slicing
-
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        inter = x.numel() * 8 * x.element_size()
-        n = x.shape[0]
-        parts = min(n, -(-inter // self.L2_SLICE_BYTES)) if self.L2_SLICE_BYTES > 0 else 1
-        if parts <= 1:
-            return _linear(self.net[2], ops.geglu(_linear(self.net[0].proj, x)))
-        out = torch.empty_like(x)
-        c = x.shape[-1]
-        w2 = wcache.cast(self.net[2], "w", self.net[2].weight, compute_dtype()).t()
-        b2 = wcache.cast(self.net[2], "b", self.net[2].bias, compute_dtype())
-        step = -(-n // parts)
-        for i in range(0, n, step):
-            g = ops.geglu(_linear(self.net[0].proj, x[i:i + step]))
-            torch.addmm(b2, g.view(-1, g.shape[-1]), w2, out=out[i:i + step].view(-1, c))
-        return out
+        # (slicing the batch so that proj -> GEGLU -> out stays inside L2 was measured slower than one pass: the smaller
+        # GEMMs lose more than the L2-resident intermediate gains; profiles/r01_ff_slice_ab.txt)
+        return _linear(self.net[2], ops.geglu(_linear(self.net[0].proj, x)))
 
 
 class BasicTransformerBlock(nn.Module):
