@@ -28,7 +28,7 @@ extern "C" {
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
 
-/* ABI version of this header (bumped on any signature change; currently 3). */
+/* ABI version of this header (bumped on any signature change; currently 5). */
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -83,6 +83,17 @@ int dadd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, con
                        int64_t chan_add_stride /* elements between samples */, void* y, int B, int C, int HW, int G, float eps, int apply_silu, int layout, int dtype,
                        void* workspace /* nullable for NCHW */, int64_t workspace_bytes, void* stream);
 
+/* GroupNorm of a channel concatenation that is never materialised: the input is [x1 | x2] along channels (the
+ * `torch.cat([hidden, skip], dim=1)` feeding every resnet of the up path, diffusers UpBlock2D / CrossAttnUpBlock2D reached
+ * through src/models/unet/unet.py:140-146); y is the normalised concatenation [B][HW][C1 + C2], NHWC, 16-bit `dtype`.
+ * x1: [B][HW][C1], x2: [B][HW][C2]; C1 % 8 == 0, C2 % 8 == 0, (C1 + C2) % G == 0.  Runs only as the one-launch cluster
+ * kernel: dadd_groupnorm_cat_supported() says whether a shape qualifies (every 256x256 UNet site does); otherwise the
+ * call fails and the caller concatenates. */
+int dadd_groupnorm_cat_supported(int B, int C1, int C2, int HW, int G, int dtype);
+int dadd_groupnorm_cat_fwd(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
+                           const float* chan_add /* nullable */, int64_t chan_add_stride, void* y, int B, int HW, int G,
+                           float eps, int apply_silu, int dtype /* DADD_BF16 | DADD_F16 */, void* stream);
+
 /* LayerNorm over the last dimension (the 48 LayerNorms of the BasicTransformerBlocks and the three of
  * src/models/feature_purifier.py:46-47,62).  x,y: [rows][C] `dtype`; gamma/beta fp32; C % 8 == 0, C <= 2048. */
 int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps,
@@ -102,8 +113,23 @@ int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out /* nullab
 int dadd_bias_residual_fwd(const void* a, const void* res /* nullable */, const float* bias /* nullable */, void* y,
                            int64_t rows, int C, int dtype, void* stream);
 
+/* Nearest-neighbour 2x upsampling of an NHWC activation: y[b][2h+i][2w+j][c] = x[b][h][w][c], i, j in {0, 1}.  Replaces
+ * F.interpolate(x, scale_factor=2.0, mode="nearest") of diffusers' Upsample2D (up path of the UNet reached through
+ * src/models/unet/unet.py:140-146, and of the VAE decoder, src/models/vae/vae.py:112).  x: [B][H][W][C], y: [B][2H][2W][C],
+ * C % 8 == 0. */
+int dadd_upsample_nearest2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+
 /* GEGLU gate of the transformer feed-forward: y[r][j] = x[r][j] * gelu_erf(x[r][inner + j]), x: [rows][2*inner]. */
 int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream);
+
+/* Feed-forward input projection fused with the GEGLU gate (tcgen05 GEMM, GELU in the epilogue):
+ *   y[m][j] = (x w[j]^T + bias[j]) * gelu_erf(x w[inner + j]^T + bias[inner + j]),  j < inner.
+ * Replaces `hidden, gate = proj(x).chunk(2, -1); hidden * F.gelu(gate)` of diffusers' GEGLU (FeedForward.net[0] of every
+ * BasicTransformerBlock reached through src/models/unet/unet.py:140-146) and the (M, 2 inner) intermediate it writes.
+ * x: [M][K], w: [2 inner][K] (nn.Linear weight layout), y: [M][inner], all 16-bit `dtype`, dense rows, 16-byte aligned;
+ * bias: fp32 [2 inner].  K % 8 == 0, inner % 128 == 0. */
+int dadd_ff_geglu_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int K, int inner,
+                      int dtype /* DADD_BF16 | DADD_F16 */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-pathway cross-attention core.
@@ -119,10 +145,13 @@ int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, v
  * o: `dtype` [B][N][*] with row stride o_stride, written at column h*d (heads merged, ready for to_out).
  * d in {40, 80, 160} (d % 8 == 0, d <= 160); seg_len % 16 == 0; n_seg*seg_len <= 64.
  * delta_scale == 0 must be expressed as n_seg = 2 (the pathway is skipped, routing_gates.py:160,177).
+ * impl: 0 = shape dispatch (N >= 128, d <= 128 and (seg_len, n_seg) in {(16,2), (16,3), (32,1)} -> tcgen05/TMEM/TMA kernel:
+ *       persistent CTAs, a query row per thread and TMEM lane, TMA ring of Q / K_cat / V_cat tiles, TMA-store epilogue;
+ *       otherwise the warp-level mma.sync kernel), 1 = force mma.sync, 2 = force tcgen05 (fails if unsupported).
  */
 int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
                         int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg, const float* gates,
-                        float scale, int dtype /* DADD_BF16 | DADD_F16 */, void* stream);
+                        float scale, int dtype /* DADD_BF16 | DADD_F16 */, int impl, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Self-attention core (attn1): o = softmax(q k^T * scale) v per (b, h), no mask.

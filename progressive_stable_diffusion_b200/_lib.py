@@ -21,11 +21,15 @@ SIGNATURES = {
     "dadd_step_begin": [_P, _P, _P, _L, _P],
     "dadd_groupnorm_workspace_bytes": [_I, _I, _I, _I, _I],
     "dadd_groupnorm_fwd": [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P, _L, _P],
+    "dadd_groupnorm_cat_supported": [_I, _I, _I, _I, _I, _I],
+    "dadd_groupnorm_cat_fwd": [_P, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _F, _I, _I, _P],
     "dadd_layernorm_fwd": [_P, _P, _P, _P, _L, _I, _F, _I, _P],
     "dadd_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "dadd_bias_residual_fwd": [_P, _P, _P, _P, _L, _I, _I, _P],
+    "dadd_upsample_nearest2x_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "dadd_ff_geglu_fwd": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "dadd_geglu_fwd": [_P, _P, _L, _I, _I, _P],
-    "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _I, _P],
+    "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _P],
     "dadd_self_attn_fwd": [_P, _P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P],
     "dadd_purifier_attn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dadd_purifier_gate_ln_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],

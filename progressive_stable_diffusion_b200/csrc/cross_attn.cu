@@ -179,13 +179,18 @@ static int launch_cross(const void* q, int64_t q_stride, const void* k_cat, cons
     return launched("dadd_cross_attn_fwd");
 }
 
+// cross_attn_tc.cu
+bool cross_attn_tc_supported(int N, int d, int seg_len, int n_seg);
+int cross_attn_tc(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o, int64_t o_stride, int B, int H,
+                  int N, int d, int seg_len, int n_seg, const float* gates, float scale, int dtype, cudaStream_t s);
+
 }  // namespace daddk
 
 using namespace daddk;
 
 extern "C" int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o,
                                    int64_t o_stride, int B, int H, int N, int d, int seg_len, int n_seg,
-                                   const float* gates, float scale, int dtype, void* stream) {
+                                   const float* gates, float scale, int dtype, int impl, void* stream) {
     DADD_REQUIRE(q && k_cat && v_cat && o && gates, "dadd_cross_attn_fwd");
     DADD_REQUIRE(dtype16_ok(dtype), "dadd_cross_attn_fwd");
     DADD_REQUIRE(B >= 0 && H > 0 && N >= 0 && B <= 65535 && H <= 65535, "dadd_cross_attn_fwd");
@@ -194,8 +199,13 @@ extern "C" int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* 
     DADD_REQUIRE(q_stride % 8 == 0 && o_stride % 8 == 0 && q_stride >= (int64_t)H * d && o_stride >= (int64_t)H * d,
                  "dadd_cross_attn_fwd");
     DADD_REQUIRE(((uintptr_t)q | (uintptr_t)k_cat | (uintptr_t)v_cat | (uintptr_t)o) % 16 == 0, "dadd_cross_attn_fwd");
+    DADD_REQUIRE(impl >= 0 && impl <= 2, "dadd_cross_attn_fwd");
     if (B == 0 || N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool tc_ok = cross_attn_tc_supported(N, d, seg_len, n_seg);
+    if (impl == 2 && !tc_ok)
+        return fail("%s: impl = 2 (tcgen05) needs N >= 128, d <= 128 and (seg_len, n_seg) in {(16,2), (16,3), (32,1)}", "dadd_cross_attn_fwd");
+    if (tc_ok && impl != 1) return cross_attn_tc(q, q_stride, k_cat, v_cat, o, o_stride, B, H, N, d, seg_len, n_seg, gates, scale, dtype, s);
 #define DADD_X(DKV) \
     DADD_DISPATCH_16(dtype, T, return (launch_cross<T, DKV>(q, q_stride, k_cat, v_cat, o, o_stride, B, H, N, d, seg_len, n_seg, gates, scale, s)))
     if (d <= 48) DADD_X(48);

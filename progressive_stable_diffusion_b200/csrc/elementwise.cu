@@ -66,9 +66,43 @@ static int launch_bias_residual(const T* a, const T* res, const float* bias, T* 
     return launched("dadd_bias_residual_fwd");
 }
 
+// Nearest-neighbour 2x upsampling of an NHWC activation (diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest")
+// ahead of its 3x3 convolution): each 16-byte input vector is read once and stored to its four output pixels.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t nvec, int W, int V) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int v = (int)(i % V);
+        const int64_t pix = i / V;
+        const int w = (int)(pix % W);
+        const int64_t bh = pix / W;                     // b * H + h
+        const uint4 t = x[i];
+        uint4* o = y + (((bh * 2) * (int64_t)(2 * W)) + 2 * w) * V + v;       // output pixel (2h, 2w)
+        const int64_t row = (int64_t)2 * W * V;
+        o[0] = t;
+        o[V] = t;
+        o[row] = t;
+        o[row + V] = t;
+    }
+}
+
 }  // namespace daddk
 
 using namespace daddk;
+
+extern "C" int dadd_upsample_nearest2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
+    DADD_REQUIRE(x && y && B >= 0 && H > 0 && W > 0, "dadd_upsample_nearest2x_fwd");
+    DADD_REQUIRE(C > 0 && C % 8 == 0, "dadd_upsample_nearest2x_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_upsample_nearest2x_fwd");
+    if (B == 0) return 0;
+    const int esz = dtype == DADD_F32 ? 4 : 2;
+    const int V = C * esz / 16;                          // 16-byte vectors per pixel (fp32: two per 8 channels)
+    const int64_t nvec = (int64_t)B * H * W * V;
+    int64_t grid = (nvec + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    upsample2x_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, nvec, W, V);
+    return launched("dadd_upsample_nearest2x_fwd");
+}
 
 extern "C" int dadd_bias_residual_fwd(const void* a, const void* res, const float* bias, void* y, int64_t rows, int C, int dtype,
                                       void* stream) {

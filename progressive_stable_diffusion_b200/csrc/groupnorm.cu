@@ -260,7 +260,8 @@ constexpr int GNC_SLAB_BUDGET = 96 * 1024;              // two CTAs per SM
 __device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <typename T>
-__global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(const T* __restrict__ x, const T* __restrict__ x2, int C1,
+                                                                    const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta,
                                                                     const float* __restrict__ chan_add, int64_t add_stride,
                                                                     T* __restrict__ y, int HW, int C, int G, float eps,
@@ -277,28 +278,46 @@ __global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(const T* __r
     float* Kg = reinterpret_cast<float*>(grp + GN_MAX_G);                                      // [G] shifts
     uint64_t* mbar = reinterpret_cast<uint64_t*>(Kg + GN_MAX_G);
 
-    const T* xs = x + (size_t)b * HW * C;
+    // two-source form (x2 != nullptr): the input is the channel concatenation [x | x2] of two NHWC tensors with C1 and
+    // C - C1 channels (the skip connections of the up path: torch.cat is never materialised); each source has its own slab
+    const int C2 = C - C1;
     const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
     const int p0 = rank * npix;
     const int my = max(0, min(npix, HW - p0));          // pixels of this CTA
     const int ms = min(my, spix);                       // ... of which staged in shared memory
-    const T* xg = xs + (size_t)p0 * C;
+    const T* xs1 = x + (size_t)b * HW * C1;
+    const T* xs2 = x2 ? x2 + (size_t)b * HW * C2 : nullptr;
+    const T* xg1 = xs1 + (size_t)p0 * C1;
+    const T* xg2 = x2 ? xs2 + (size_t)p0 * C2 : nullptr;
     T* yg = y + ((size_t)b * HW + p0) * C;
+    T* slab2 = slab + (size_t)spix * C1;
+    // this thread's column: source, row stride and base pointers
+    const bool second = c0 >= C1;
+    const int sC = second ? C2 : C1;
+    const T* sl = second ? slab2 + (c0 - C1) : slab + c0;
+    const T* xg = second ? xg2 + (c0 - C1) : xg1 + c0;
 
     if (tid == 0) {      // the slab copy goes out first: everything else overlaps with it
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gn_smem_u32(mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t total = (uint32_t)((size_t)ms * C * sizeof(T));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gn_smem_u32(mbar)), "r"(total) : "memory");
-        for (uint32_t off = 0; off < total; off += 32768u) {
-            const uint32_t n = min(32768u, total - off);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(gn_smem_u32(gn_smem + off)), "l"(reinterpret_cast<const unsigned char*>(xg) + off), "r"(n),
-                           "r"(gn_smem_u32(mbar))
-                         : "memory");
+        for (int src = 0; src < (x2 ? 2 : 1); ++src) {
+            const uint32_t bytes = (uint32_t)((size_t)ms * (src ? C2 : C1) * sizeof(T));
+            const unsigned char* g = reinterpret_cast<const unsigned char*>(src ? xg2 : xg1);
+            unsigned char* d = reinterpret_cast<unsigned char*>(src ? slab2 : slab);
+            for (uint32_t off = 0; off < bytes; off += 32768u) {
+                const uint32_t n = min(32768u, bytes - off);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(gn_smem_u32(d + off)), "l"(g + off), "r"(n), "r"(gn_smem_u32(mbar))
+                             : "memory");
+            }
         }
     }
-    if (tid < G) Kg[tid] = to_f(xs[tid * cpg]) + (addb ? addb[tid * cpg] : 0.0f);
+    if (tid < G) {
+        const int cg = tid * cpg;
+        Kg[tid] = to_f(cg < C1 ? xs1[cg] : xs2[cg - C1]) + (addb ? addb[cg] : 0.0f);
+    }
     __syncthreads();
     // per-thread constants while the copies fly
     const int g0 = c0 / cpg;
@@ -333,26 +352,26 @@ __global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(const T* __r
         int p = ph;
         for (; p + PH < ms; p += 2 * PH) {
             Vec8<T> t0, t1;
-            t0.load(slab + (size_t)p * C + c0);
-            t1.load(slab + (size_t)(p + PH) * C + c0);
+            t0.load(sl + (size_t)p * sC);
+            t1.load(sl + (size_t)(p + PH) * sC);
             acc(t0);
             acc(t1);
         }
         for (; p < ms; p += PH) {
             Vec8<T> t0;
-            t0.load(slab + (size_t)p * C + c0);
+            t0.load(sl + (size_t)p * sC);
             acc(t0);
         }
         for (; p + PH < my; p += 2 * PH) {               // streamed remainder (p >= spix)
             Vec8<T> t0, t1;
-            t0.load(xg + (size_t)p * C + c0);
-            t1.load(xg + (size_t)(p + PH) * C + c0);
+            t0.load(xg + (size_t)p * sC);
+            t1.load(xg + (size_t)(p + PH) * sC);
             acc(t0);
             acc(t1);
         }
         for (; p < my; p += PH) {
             Vec8<T> t0;
-            t0.load(xg + (size_t)p * C + c0);
+            t0.load(xg + (size_t)p * sC);
             acc(t0);
         }
     }
@@ -432,26 +451,26 @@ __global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(const T* __r
         int p = ph;
         for (; p + PH < ms; p += 2 * PH) {
             Vec8<T> t0, t1;
-            t0.load(slab + (size_t)p * C + c0);
-            t1.load(slab + (size_t)(p + PH) * C + c0);
+            t0.load(sl + (size_t)p * sC);
+            t1.load(sl + (size_t)(p + PH) * sC);
             gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
             gn_emit(t1, sa, sb, apply_silu, yg + (size_t)(p + PH) * C + c0);
         }
         for (; p < ms; p += PH) {
             Vec8<T> t0;
-            t0.load(slab + (size_t)p * C + c0);
+            t0.load(sl + (size_t)p * sC);
             gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
         }
         for (; p + PH < my; p += 2 * PH) {
             Vec8<T> t0, t1;
-            t0.load(xg + (size_t)p * C + c0);
-            t1.load(xg + (size_t)(p + PH) * C + c0);
+            t0.load(xg + (size_t)p * sC);
+            t1.load(xg + (size_t)(p + PH) * sC);
             gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
             gn_emit(t1, sa, sb, apply_silu, yg + (size_t)(p + PH) * C + c0);
         }
         for (; p < my; p += PH) {
             Vec8<T> t0;
-            t0.load(xg + (size_t)p * C + c0);
+            t0.load(xg + (size_t)p * sC);
             gn_emit(t0, sa, sb, apply_silu, yg + (size_t)p * C + c0);
         }
     }
@@ -489,9 +508,10 @@ static GncPlan gnc_plan(int B, int C, int HW, int G, size_t esize) {
 }
 
 template <typename T>
-static int launch_cluster(const GncPlan& p, const T* x, const float* gamma, const float* beta, const float* chan_add,
+static int launch_cluster(const GncPlan& p, const T* x, const T* x2, int C1, const float* gamma, const float* beta, const float* chan_add,
                           int64_t add_stride, T* y, int B, int C, int HW, int G, float eps, int silu, cudaStream_t s) {
-    DADD_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "dadd_groupnorm_fwd(NHWC)");
+    DADD_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(x2) & 15) == 0, "dadd_groupnorm_fwd(NHWC)");
     auto kern = gn_cluster_kernel<T>;
     static bool configured = false;       // per template instance
     if (!configured) {
@@ -510,7 +530,7 @@ static int launch_cluster(const GncPlan& p, const T* x, const float* gamma, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, x, gamma, beta, chan_add, add_stride, y, HW, C, G, eps, silu, p.npix, p.spix, p.S);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, x, x2, C1, gamma, beta, chan_add, add_stride, y, HW, C, G, eps, silu, p.npix, p.spix, p.S);
     if (e != cudaSuccess) return cuda_ok(e, "dadd_groupnorm_fwd(NHWC cluster) launch");
     return launched("dadd_groupnorm_fwd(NHWC cluster)");
 }
@@ -627,7 +647,7 @@ static int launch_nhwc(const T* x, const float* gamma, const float* beta, const 
     DADD_REQUIRE(C / 8 <= 512, "dadd_groupnorm_fwd(NHWC)");
     static const bool force_flat = [] { const char* e = getenv("DADD_GN_FLAT"); return e && atoi(e) != 0; }();
     const GncPlan cp = gnc_plan(B, C, HW, G, sizeof(T));
-    if (cp.ok && !force_flat) return launch_cluster(cp, x, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, s);
+    if (cp.ok && !force_flat) return launch_cluster(cp, x, (const T*)nullptr, C, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, s);
     DADD_REQUIRE(workspace != nullptr && workspace_bytes >= gn_workspace_bytes(B, C, HW, G), "dadd_groupnorm_fwd(NHWC)");
     DADD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dadd_groupnorm_fwd(NHWC)");
     const GnPlan p = gn_plan(B, C, HW);
@@ -693,3 +713,36 @@ extern "C" int dadd_groupnorm_fwd(const void* x, const float* gamma, const float
     DADD_DISPATCH_ANY(dtype, T, return launch_nchw((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
     return 1;
 }
+
+static bool gn_cat_plan(int B, int C1, int C2, int HW, int G, int dtype, GncPlan* out) {
+    if (B <= 0 || C1 <= 0 || C2 <= 0 || HW <= 0 || G <= 0 || G > GN_MAX_G) return false;
+    if (C1 % 8 != 0 || C2 % 8 != 0 || (C1 + C2) % G != 0 || !dtype16_ok(dtype)) return false;
+    static const bool force_flat = [] { const char* e = getenv("DADD_GN_FLAT"); return e && atoi(e) != 0; }();
+    const GncPlan cp = gnc_plan(B, C1 + C2, HW, G, 2);
+    if (out) *out = cp;
+    return cp.ok && !force_flat;
+}
+
+extern "C" int dadd_groupnorm_cat_supported(int B, int C1, int C2, int HW, int G, int dtype) {
+    return gn_cat_plan(B, C1, C2, HW, G, dtype, nullptr) ? 1 : 0;
+}
+
+extern "C" int dadd_groupnorm_cat_fwd(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
+                                      const float* chan_add, int64_t chan_add_stride, void* y, int B, int HW, int G, float eps,
+                                      int apply_silu, int dtype, void* stream) {
+    DADD_REQUIRE(x1 && x2 && y && gamma && beta, "dadd_groupnorm_cat_fwd");
+    DADD_REQUIRE(B >= 0, "dadd_groupnorm_cat_fwd");
+    if (B == 0) return 0;
+    GncPlan cp;
+    if (!gn_cat_plan(B, C1, C2, HW, G, dtype, &cp))
+        return fail("%s: shape not supported by the one-launch cluster kernel (C1 + C2 = %lld, HW = %lld): check "
+                    "dadd_groupnorm_cat_supported() and concatenate on the caller's side", "dadd_groupnorm_cat_fwd",
+                    (long long)C1 + C2, (long long)HW);
+    cudaStream_t s = (cudaStream_t)stream;
+    static const bool silu_exact = [] { const char* e = getenv("DADD_SILU_EXACT"); return e && atoi(e) != 0; }();
+    if (apply_silu) apply_silu = silu_exact ? 1 : 2;
+    DADD_DISPATCH_16(dtype, T, return launch_cluster(cp, (const T*)x1, (const T*)x2, C1, gamma, beta, chan_add, chan_add_stride, (T*)y, B,
+                                                     C1 + C2, HW, G, eps, apply_silu, s));
+    return 1;
+}
+

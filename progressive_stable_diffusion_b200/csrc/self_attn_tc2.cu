@@ -64,6 +64,36 @@ __device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// 2^a for a pair of exponents on the FMA / ALU pipes instead of the MUFU pipe (the bound of this kernel at d = 40 is the
+// 16 exp2 per clock per SM of the MUFU unit; the FMA pipe is mostly idle): a is clamped to >= -125, rounded to the nearest
+// integer n with the 1.5 * 2^23 trick, 2^(a - n) is a degree-3 minimax polynomial on [-0.5, 0.5] (max relative error
+// 7.5e-5, far below the 2^-9 / 2^-11 rounding of the 16-bit P it feeds) and n is added into the exponent field with one
+// integer shift-add.  Valid for a <= +126 (the lazy rescale keeps a <= 8).
+__device__ __forceinline__ void exp2_poly2(uint64_t a, float& p0, float& p1) {
+    float a0, a1;
+    unpack_f2(a, a0, a1);
+    a0 = fmaxf(a0, -125.0f);
+    a1 = fmaxf(a1, -125.0f);
+    const uint64_t ac = pack_f2(a0, a1);
+    const uint64_t t = add_f2(ac, pack_f2(12582912.0f, 12582912.0f));
+    const uint64_t n = add_f2(t, pack_f2(-12582912.0f, -12582912.0f));
+    const uint64_t f = fma_f2(n, pack_f2(-1.0f, -1.0f), ac);
+    uint64_t p = fma_f2(pack_f2(0.055171459913253784f, 0.055171459913253784f), f, pack_f2(0.2426108568906784f, 0.2426108568906784f));
+    p = fma_f2(p, f, pack_f2(0.6932609677314758f, 0.6932609677314758f));
+    p = fma_f2(p, f, pack_f2(0.9999281167984009f, 0.9999281167984009f));
+    float t0, t1;
+    unpack_f2(p, p0, p1);
+    unpack_f2(t, t0, t1);
+    p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+// which of the 4 pairs of exp2 batch `bt` (8 exponentials) go to the polynomial: POLY = pairs per 2 batches (0..8)
+template <int POLY>
+__device__ __forceinline__ constexpr bool poly_pair(int bt, int k) {
+    const int even = (POLY + 1) / 2, odd = POLY / 2;      // pairs in even / odd batches
+    return k < ((bt & 1) ? odd : even);
+}
+
 // descriptor with the start address advanced by `bytes` (the address field holds addr >> 4 in bits [0,14): no carry out
 // for shared-memory addresses below 256 KB)
 __device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
@@ -87,7 +117,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
         }                                                                                           \
     } while (0)
 
-template <typename T, int NP, int BN_, int STAGES, bool TRACE>
+template <typename T, int NP, int BN_, int STAGES, bool TRACE, int POLY>
 __global__ void __launch_bounds__(NTHREADS, 1)
 self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, int B, int H, int N, int d,
@@ -276,7 +306,8 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
                 DADD_TRACE_EVENT(q, s, 2);
                 fence_before();
                 mbar_arrive(&bars->s_read[q]);                       // S_q may be overwritten by the next QK^T
-                if ((j + 1) * BN_ > N) {                             // ragged last key tile
+                const bool ragged = (j + 1) * BN_ > N;
+                if (ragged) {                                        // ragged last key tile
 #pragma unroll
                     for (int i = 0; i < BN_; ++i)
                         if (j * BN_ + i >= N) sr[i] = 0xff800000u;   // -inf
@@ -334,39 +365,52 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
                 DADD_TRACE_EVENT(q, s, 5);
                 // Software-pipelined in batches of 8: the exp2 of batch b are issued back to back while the results of batch
                 // b-1 (long in flight) are summed, converted and stored, so ONE warp per scheduler keeps the MUFU pipe busy.
-                {
+                auto exp_phase = [&](auto poly_tag) {
+                    constexpr int POLYX = decltype(poly_tag)::value;
                     constexpr int NB = BN_ / 8;
                     float pprev[8], pcur[8];
                     uint32_t pk[16];
-                    auto scaled = [&](int base, float (&a)[8]) {
+                    auto scaled = [&](int base, uint64_t (&a)[4]) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            unpack_f2(fma_f2(pack_f2(__uint_as_float(sr[base + 2 * k]), __uint_as_float(sr[base + 2 * k + 1])), ccx, nb),
-                                      a[2 * k], a[2 * k + 1]);
+                            a[k] = fma_f2(pack_f2(__uint_as_float(sr[base + 2 * k]), __uint_as_float(sr[base + 2 * k + 1])), ccx, nb);
+                    };
+                    // pair k of batch bt: MUFU, or the FMA-pipe polynomial for a fixed share of the pairs (a ragged tile runs
+                    // the all-MUFU instance: its masked -inf scores must map to exactly 0)
+                    auto expo = [&](int bt, int k, uint64_t a, float& p0, float& p1) {
+                        if (poly_pair<POLYX>(bt, k)) {
+                            exp2_poly2(a, p0, p1);
+                        } else {
+                            float a0, a1;
+                            unpack_f2(a, a0, a1);
+                            p0 = ex2(a0);
+                            p1 = ex2(a1);
+                        }
                     };
                     {
-                        float a[8];
+                        uint64_t a[4];
                         scaled(0, a);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) pprev[i] = ex2(a[i]);
+                        for (int k = 0; k < 4; ++k) expo(0, k, a[k], pprev[2 * k], pprev[2 * k + 1]);
                     }
 #pragma unroll
                     for (int bt = 1; bt <= NB; ++bt) {
-                        float a[8];
+                        uint64_t a[4];
                         if (bt < NB) scaled(bt * 8, a);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (bt < NB) pcur[i] = ex2(a[i]);
-                            if (i & 1) {                              // retire one pair of the previous batch per two exp2 issued
-                                acc[(i >> 1) & 3] = add_f2(acc[(i >> 1) & 3], pack_f2(pprev[i - 1], pprev[i]));
-                                pk[(((bt - 1) * 8 + i) >> 1) & 15] = pack2<T>(pprev[i - 1], pprev[i]);
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            if (bt < NB) expo(bt, k, a[k], pcur[2 * k], pcur[2 * k + 1]);
+                            const int i = 2 * k + 1;                  // retire one pair of the previous batch per pair issued
+                            acc[k] = add_f2(acc[k], pack_f2(pprev[i - 1], pprev[i]));
+                            pk[(((bt - 1) * 8 + i) >> 1) & 15] = pack2<T>(pprev[i - 1], pprev[i]);
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pprev[i] = pcur[i];
                         if ((bt & 3) == 0) tmem_st16(tP + (bt / 4 - 1) * 16, pk);   // 32 probabilities = 16 packed columns done
                     }
-                }
+                };
+                if (POLY > 0 && !ragged) exp_phase(std::integral_constant<int, POLY>{});
+                else exp_phase(std::integral_constant<int, 0>{});
                 if (q == 0 || s + 1 < steps) named_arrive(2 - q, 256);   // the other group's turn (none left after the last step)
                 DADD_TRACE_EVENT(q, s, 6);
                 {
@@ -429,7 +473,7 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     }
 }
 
-template <typename T, int NP, int BN_, int STAGES>
+template <typename T, int NP, int BN_, int STAGES, int POLY>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int B, int H, int N,
                   int d, float scale, cudaStream_t s) {
     const size_t smem = (size_t)4 * NP * 128 * 128 + (size_t)2 * STAGES * NP * BN_ * 128 + sizeof(Bars<STAGES>) + 1024;
@@ -440,7 +484,7 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
         // debugging aid: DADD_ATTN_TRACE=<file> dumps CTA 0's event timeline of every launch (synchronises; never in a product run)
         static const char* trace_path = getenv("DADD_ATTN_TRACE");
         if (trace_path) {
-            auto tk_ = self_attn_tc2_kernel<T, NP, BN_, STAGES, true>;
+            auto tk_ = self_attn_tc2_kernel<T, NP, BN_, STAGES, true, POLY>;
             if (cuda_ok(cudaFuncSetAttribute(tk_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "self_attn_tc2 smem")) return 2;
             long long* buf = nullptr;
             const size_t n = 3 * 64 * 16;
@@ -459,7 +503,7 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
             return launched("dadd_self_attn_fwd(tcgen05 v2 trace)");
         }
     }
-    auto kern = self_attn_tc2_kernel<T, NP, BN_, STAGES, false>;
+    auto kern = self_attn_tc2_kernel<T, NP, BN_, STAGES, false, POLY>;
     if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "self_attn_tc2 smem")) return 2;
     kern<<<grid, NTHREADS, smem, s>>>(tq, tk, tv, to, B, H, N, d, sl2, nullptr);
     return launched("dadd_self_attn_fwd(tcgen05 v2)");
@@ -477,9 +521,17 @@ int self_attn_tc2(const void* q, const void* k, const void* v, int64_t qs, int64
     if (tc::make_map(&tq, q, qs, B, H, N, d, dtype, 128) || tc::make_map(&tk, k, ks, B, H, N, d, dtype, bn) ||
         tc::make_map(&tv, v, vs, B, H, N, d, dtype, bn) || tc::make_map(&to, o, os, B, H, N, d, dtype, 128))
         return 1;
-#define DADD_TC2(NPV, BNV, STG) DADD_DISPATCH_16(dtype, T, return (tc2::launch<T, NPV, BNV, STG>(tq, tk, tv, to, B, H, N, d, scale, s)))
-    if (np == 1) DADD_TC2(1, 128, 4);
-    DADD_TC2(2, 64, 3);
+    // Share of the exponentials computed by the FMA-pipe polynomial, in pairs per 16.  Measured on B200 (N = 1024, d = 40,
+    // B = 26): 0 -> 86.4 us, 2 -> 87.8, 3 -> 91.5, 4 -> 99.5 (profiles/r01_attn_poly_exp.txt): on sm_100a FFMA2/FADD2 issue at
+    // half rate, so the polynomial costs the FMA pipe as many cycles per element as MUFU.EX2 costs the XU pipe and the
+    // softmax warps (one per scheduler and turn) become issue-bound.  Default 0; DADD_ATTN_POLY=2 selects the mixed variant.
+    static const int poly = getenv("DADD_ATTN_POLY") ? atoi(getenv("DADD_ATTN_POLY")) : 0;
+#define DADD_TC2(NPV, BNV, STG, PL) DADD_DISPATCH_16(dtype, T, return (tc2::launch<T, NPV, BNV, STG, PL>(tq, tk, tv, to, B, H, N, d, scale, s)))
+    if (np == 1) {
+        if (poly == 2) DADD_TC2(1, 128, 4, 2);
+        DADD_TC2(1, 128, 4, 0);
+    }
+    DADD_TC2(2, 64, 3, 0);
 #undef DADD_TC2
     return 1;
 }

@@ -110,6 +110,43 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, num_gro
     return y
 
 
+def group_norm_cat_supported(x1: torch.Tensor, x2: torch.Tensor, num_groups: int) -> bool:
+    b, c1, h, w = x1.shape
+    return (x1.dtype in (torch.bfloat16, torch.float16) and x1.is_contiguous(memory_format=torch.channels_last)
+            and x2.is_contiguous(memory_format=torch.channels_last)
+            and bool(_lib.load().dadd_groupnorm_cat_supported(b, c1, x2.shape[1], h * w, num_groups, _dt(x1))))
+
+
+def group_norm_cat(x1: torch.Tensor, x2: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, num_groups: int, eps: float,
+                   silu: bool, chan_add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) of ``torch.cat([x1, x2], dim=1)`` without materialising the concatenation (channels_last, 16-bit)."""
+    _cuda(x1, x2, gamma, beta, chan_add)
+    b, c1, h, w = x1.shape
+    c2 = x2.shape[1]
+    assert x2.shape == (b, c2, h, w) and x1.dtype == x2.dtype
+    assert x1.is_contiguous(memory_format=torch.channels_last) and x2.is_contiguous(memory_format=torch.channels_last)
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == c1 + c2
+    if chan_add is not None:
+        assert chan_add.dtype == torch.float32 and chan_add.shape == (b, c1 + c2) and chan_add.stride(1) == 1
+    y = torch.empty((b, c1 + c2, h, w), dtype=x1.dtype, device=x1.device, memory_format=torch.channels_last)
+    _lib.check(_lib.load().dadd_groupnorm_cat_fwd(x1.data_ptr(), c1, x2.data_ptr(), c2, gamma.data_ptr(), beta.data_ptr(),
+                                                  _ptr(chan_add), 0 if chan_add is None else chan_add.stride(0), y.data_ptr(),
+                                                  b, h * w, num_groups, eps, int(silu), _dt(x1), _stream()),
+               "dadd_groupnorm_cat_fwd")
+    return y
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    """``F.interpolate(x, scale_factor=2.0, mode="nearest")`` for a channels_last ``(B, C, H, W)`` tensor."""
+    _cuda(x)
+    b, c, h, w = x.shape
+    assert x.is_contiguous(memory_format=torch.channels_last)
+    y = torch.empty((b, c, 2 * h, 2 * w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    _lib.check(_lib.load().dadd_upsample_nearest2x_fwd(x.data_ptr(), y.data_ptr(), b, h, w, c, _dt(x), _stream()),
+               "dadd_upsample_nearest2x_fwd")
+    return y
+
+
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     _cuda(x, gamma, beta)
     assert x.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
@@ -171,6 +208,20 @@ def geglu(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def ff_geglu(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``h, g = F.linear(x, w, bias).chunk(2, -1); h * gelu(g)`` as one tcgen05 GEMM with the gate in its epilogue.
+    x (..., K) 16-bit contiguous, w (2*inner, K) same dtype, bias (2*inner,) fp32 -> (..., inner)."""
+    _cuda(x, w, bias)
+    k = x.shape[-1]
+    inner = w.shape[0] // 2
+    assert x.is_contiguous() and w.is_contiguous() and w.shape == (2 * inner, k) and w.dtype == x.dtype
+    assert x.dtype in (torch.bfloat16, torch.float16) and bias.dtype == torch.float32 and bias.numel() == 2 * inner
+    y = torch.empty(*x.shape[:-1], inner, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().dadd_ff_geglu_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), x.numel() // k, k, inner,
+                                             _dt(x), _stream()), "dadd_ff_geglu_fwd")
+    return y
+
+
 # --------------------------------------------------------------------------------------------- attention
 def _rows(t: torch.Tensor) -> int:
     """Row stride (elements) of a (B, N, *) view whose last dim is dense and whose batch stride is N * row stride."""
@@ -180,8 +231,9 @@ def _rows(t: torch.Tensor) -> int:
 
 
 def cross_attention(q: torch.Tensor, k_cat: torch.Tensor, v_cat: torch.Tensor, gates: torch.Tensor, heads: int,
-                    seg_len: int, n_seg: int, scale: Optional[float] = None) -> torch.Tensor:
-    """sum_s gates[s] softmax(q k_s^T scale) v_s; q (B,N,H*d) bf16 (may be a strided view), k_cat/v_cat (B,H,L,d)."""
+                    seg_len: int, n_seg: int, scale: Optional[float] = None, impl: str = "auto") -> torch.Tensor:
+    """sum_s gates[s] softmax(q k_s^T scale) v_s; q (B,N,H*d) bf16 (may be a strided view), k_cat/v_cat (B,H,L,d).
+    ``impl``: "auto" (tcgen05 kernel for N >= 128, d <= 128), "mma" or "tc"."""
     _cuda(q, k_cat, v_cat, gates)
     b, n, c = q.shape
     d = c // heads
@@ -191,7 +243,8 @@ def cross_attention(q: torch.Tensor, k_cat: torch.Tensor, v_cat: torch.Tensor, g
     o = torch.empty(b, n, c, device=q.device, dtype=q.dtype)
     _lib.check(_lib.load().dadd_cross_attn_fwd(q.data_ptr(), _rows(q), k_cat.data_ptr(), v_cat.data_ptr(), o.data_ptr(), c,
                                                b, heads, n, d, seg_len, n_seg, gates.data_ptr(),
-                                               float(d ** -0.5 if scale is None else scale), _dt(q), _stream()),
+                                               float(d ** -0.5 if scale is None else scale), _dt(q),
+                                               {"auto": 0, "mma": 1, "tc": 2}[impl], _stream()),
                "dadd_cross_attn_fwd")
     return o
 

@@ -60,10 +60,20 @@ def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, w, b)
 
 
-def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor, extra_bias: Optional[nn.Module] = None) -> torch.Tensor:
+def _conv1x1_weight(mod: nn.Conv2d, cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """(C_out, C_in) 16-bit GEMM weight of a 1x1 convolution, or the contiguous copy of its input columns [lo, hi)."""
+    if cols is None:
+        return wcache.get(mod, "w2d", (mod.weight,), lambda: mod.weight.detach().to(compute_dtype()).reshape(mod.out_channels, -1).contiguous())
+    lo, hi = cols
+    return wcache.get(mod, f"w2d[{lo}:{hi}]", (mod.weight,),
+                      lambda: mod.weight.detach().to(compute_dtype()).reshape(mod.out_channels, -1)[:, lo:hi].contiguous())
+
+
+def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor, extra_bias: Optional[nn.Module] = None,
+                       cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """1x1 convolution as a GEMM on channels-last tokens (bias in the GEMM epilogue).  ``extra_bias``: a module whose bias
-    is added on top (a resnet's conv2 bias rides on its shortcut GEMM)."""
-    w = wcache.get(mod, "w2d", (mod.weight,), lambda: mod.weight.detach().to(compute_dtype()).reshape(mod.out_channels, -1).contiguous())
+    is added on top (a resnet's conv2 bias rides on its shortcut GEMM).  ``cols``: use only these input channels."""
+    w = _conv1x1_weight(mod, cols)
     if extra_bias is None:
         b = wcache.cast(mod, "b", mod.bias, compute_dtype())
     else:
@@ -155,7 +165,12 @@ class FeedForward(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         # (slicing the batch so that proj -> GEGLU -> out stays inside L2 was measured slower than one pass: the smaller
         # GEMMs lose more than the L2-resident intermediate gains; profiles/r01_ff_slice_ab.txt)
-        return _linear(self.net[2], ops.geglu(_linear(self.net[0].proj, x)))
+        proj = self.net[0].proj
+        if proj.out_features % 256 == 0 and x.is_contiguous():       # (M, 8C) projection + GEGLU in one tcgen05 GEMM
+            g = ops.ff_geglu(x, wcache.cast(proj, "w", proj.weight, compute_dtype()), _bias32(proj))
+        else:
+            g = ops.geglu(_linear(proj, x))
+        return _linear(self.net[2], g)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -207,19 +222,36 @@ class ResnetBlock2D(nn.Module):
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
-    def forward(self, x: torch.Tensor, temb_term: Optional[torch.Tensor]) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, temb_term: Optional[torch.Tensor], skip: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``temb_term`` = time_emb_proj(silu(emb)) + conv1.bias as fp32 (B, cout) (``UNet2DConditionModel.time_terms``):
         folded into norm2's input by the GN kernel.  No convolution adds its own bias: conv1's rides on ``temb_term``,
-        conv2's on the residual add (or on the shortcut GEMM's epilogue)."""
-        h = _conv_nobias(self.conv1, _gn(self.norm1, x, silu=True))
+        conv2's on the residual add (or on the shortcut GEMM's epilogue).
+
+        ``skip``: the block input is ``cat([x, skip], dim=1)`` (up path).  The concatenation is never written: norm1 reads
+        both tensors (``dadd_groupnorm_cat_fwd``) and the 1x1 shortcut is two accumulating GEMMs over the two halves of
+        its weight."""
+        if skip is not None and not ops.group_norm_cat_supported(x, skip, self.norm1.num_groups):
+            x, skip = torch.cat([x, skip], dim=1), None
+        if skip is not None:
+            n1 = ops.group_norm_cat(x, skip, wcache.cast(self.norm1, "w", self.norm1.weight, torch.float32),
+                                    wcache.cast(self.norm1, "b", self.norm1.bias, torch.float32), self.norm1.num_groups,
+                                    self.norm1.eps, True)
+        else:
+            n1 = _gn(self.norm1, x, silu=True)
+        h = _conv_nobias(self.conv1, n1)
         if temb_term is None:                                       # VAE resnets: only conv1's bias, one row for all samples
             temb_term = _bias32(self.conv1).view(1, -1).expand(x.shape[0], -1)
         h = _conv_nobias(self.conv2, _gn(self.norm2, h, silu=True, chan_add=temb_term))
         if self.conv_shortcut is None:
             return ops.bias_residual(h, x, _bias32(self.conv2), out=h)
-        b, _, hh, ww = x.shape
-        sc = _image(_conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2), hh, ww)
-        return ops.bias_residual(h, sc, out=h)
+        b, c1, hh, ww = x.shape
+        if skip is None:
+            sc = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2)
+        else:
+            sc = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2, cols=(0, c1))
+            w2 = _conv1x1_weight(self.conv_shortcut, (c1, c1 + skip.shape[1]))
+            sc.view(-1, sc.shape[-1]).addmm_(_tokens(skip).reshape(-1, skip.shape[1]), w2.t())
+        return ops.bias_residual(h, _image(sc, hh, ww), out=h)
 
 
 class Downsample2D(nn.Module):
@@ -237,7 +269,7 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
     def forward(self, x):
-        return _conv(self.conv, F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        return _conv(self.conv, ops.upsample_nearest2x(x))
 
 
 class _Block(nn.Module):
@@ -397,8 +429,7 @@ class UNet2DConditionModel(nn.Module):
         x = mb.resnets[1](x, terms[id(mb.resnets[1])])
         for blk in self.up_blocks:
             for j, res in enumerate(blk.resnets):
-                x = torch.cat([x, skips.pop()], dim=1)
-                x = res(x, terms[id(res)])
+                x = res(x, terms[id(res)], skip=skips.pop())
                 if len(blk.attentions) > 0:
                     x = blk.attentions[j](x, ehs)
             if blk.upsamplers is not None:

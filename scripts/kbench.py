@@ -122,8 +122,9 @@ if on("cross"):
         q = torch.randn(B, N, C, device=dev, dtype=dt)
         kc = torch.randn(B, 8, 48, C // 8, device=dev, dtype=dt)
         vc = torch.randn(B, 8, 48, C // 8, device=dev, dtype=dt)
-        us, mn = timeit(lambda: ops.cross_attention(q, kc, vc, gates, 8, 16, 3))
-        report(f"cross_attn N={N} C={C} B={B}", us, mn, bytes_=4.0 * N * C * B + 2 * 2.0 * B * 48 * C)
+        impl = os.environ.get("KBENCH_XATTN_IMPL", "auto")
+        us, mn = timeit(lambda: ops.cross_attention(q, kc, vc, gates, 8, 16, 3, impl=impl))
+        report(f"cross_attn[{impl}] N={N} C={C} B={B}", us, mn, bytes_=4.0 * N * C * B + 2 * 2.0 * B * 48 * C)
 
 if on("gn"):
     shapes = [(320, R), (640, R), (960, R), (640, R // 2), (1280, R // 2), (1920, R // 2), (1280, R // 4), (2560, R // 4),
@@ -150,6 +151,19 @@ if on("geglu"):
         x = torch.randn(B, N, 8 * C, device=dev, dtype=dt)
         us, mn = timeit(lambda: ops.geglu(x))
         report(f"geglu N={N} C={C} B={B}", us, mn, bytes_=2.0 * x.numel() * 1.5)
+
+if on("ff1"):
+    import torch.nn.functional as F
+    for C, N in sites:
+        x = torch.randn(B, N, C, device=dev, dtype=dt)
+        w = torch.randn(8 * C, C, device=dev, dtype=dt) * (C ** -0.5)
+        b32 = torch.randn(8 * C, device=dev)
+        b16 = b32.to(dt)
+        flops = 2.0 * B * N * C * 8 * C
+        us, mn = timeit(lambda: ops.geglu(F.linear(x, w, b16)))
+        report(f"ff1 library GEMM + geglu N={N} C={C} B={B}", us, mn, flops=flops)
+        us, mn = timeit(lambda: ops.ff_geglu(x, w, b32))
+        report(f"ff1 fused tcgen05 N={N} C={C} B={B}", us, mn, flops=flops)
 
 if on("add_ln"):
     for C, N in sites:

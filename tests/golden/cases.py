@@ -14,6 +14,11 @@ PROCESSOR_CASES = [
     dict(name="base_d40_both", kind="base", c=320, n=64, b=2, mode="both", seed=15),
     dict(name="base_d80_img", kind="base", c=640, n=32, b=1, mode="image_dominant", seed=16),
     dict(name="base_d160_aoe", kind="base", c=1280, n=16, b=1, mode="aoe_dominant", seed=17),
+    # N >= 128: the tcgen05 cross-attention kernel (full tiles, a ragged last tile, 2 / 3 segments, one 32-token segment)
+    dict(name="split_d40_n256_l3", kind="split", c=320, n=256, b=1, gates=(0.1, 0.9), delta_scale=3.0, seed=18),
+    dict(name="split_d80_n136_l3", kind="split", c=640, n=136, b=1, gates=(0.9, 0.1), delta_scale=2.0, seed=19),
+    dict(name="split_d40_n128_l0", kind="split", c=320, n=128, b=1, gates=(0.3, 0.7), delta_scale=0.0, seed=20),
+    dict(name="base_d40_n192_both", kind="base", c=320, n=192, b=1, mode="both", seed=21),
 ]
 
 

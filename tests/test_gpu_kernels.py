@@ -134,6 +134,46 @@ def test_groupnorm_expanded_chan_add_row():
     assert (y.float().cpu() - ref).abs().max().item() < 0.04
 
 
+# the 12 skip concatenations of the up path (C_hidden, C_skip, side) at 256x256, plus a 512x512 site (flat path -> not supported)
+GN_CAT_SHAPES = [(1280, 1280, 4), (1280, 1280, 8), (1280, 640, 8), (1280, 640, 16), (640, 640, 16), (640, 320, 16),
+                 (640, 320, 32), (320, 320, 32)]
+
+
+@pytest.mark.parametrize("c1,c2,hw", GN_CAT_SHAPES)
+@pytest.mark.parametrize("b", [3, 26])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_groupnorm_cat_equals_groupnorm_of_concatenation(c1, c2, hw, b, dtype):
+    """dadd_groupnorm_cat_fwd([x1 | x2]) must equal dadd_groupnorm_fwd(torch.cat) BIT FOR BIT (same kernel, same arithmetic,
+    only the addressing differs) and match the fp32 reference."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(c1 + c2 + hw + b)
+    x1 = (torch.randn(b, c1, hw, hw, generator=g) * 1.5 + 0.7).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    x2 = (torch.randn(b, c2, hw, hw, generator=g) * 0.6 - 0.4).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    c = c1 + c2
+    gamma, beta = (1 + 0.2 * torch.randn(c, generator=g)).to(DEV), (0.2 * torch.randn(c, generator=g)).to(DEV)
+    add = torch.randn(b, c, generator=g).to(DEV)
+    assert ops.group_norm_cat_supported(x1, x2, 32)
+    cat = torch.cat([x1, x2], dim=1).contiguous(memory_format=torch.channels_last)
+    for silu, use_add in ((True, False), (True, True), (False, False)):
+        want = ops.group_norm(cat, gamma, beta, 32, 1e-5, silu, add if use_add else None)
+        got = ops.group_norm_cat(x1, x2, gamma, beta, 32, 1e-5, silu, add if use_add else None)
+        assert got.shape == want.shape and got.stride() == want.stride()
+        assert torch.equal(got, want), (c1, c2, hw, silu, use_add, (got.float() - want.float()).abs().max().item())
+    ref = F.group_norm(cat.float().cpu(), 32, gamma.cpu(), beta.cpu(), 1e-5)       # the last combination: no SiLU, no add
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    assert (got.float().cpu() - ref).abs().max().item() <= ulp * max(1.0, ref.abs().max().item())
+
+
+def test_groupnorm_cat_rejects_shapes_outside_the_cluster_kernel():
+    ops = _ops()
+    from progressive_stable_diffusion_b200._lib import DaddError
+    x1 = torch.zeros(1, 640, 64, 64, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    x2 = torch.zeros(1, 320, 64, 64, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    assert not ops.group_norm_cat_supported(x1, x2, 32)          # 7.9 MB per sample: the flat multi-pass path, caller concatenates
+    with pytest.raises(DaddError):
+        ops.group_norm_cat(x1, x2, torch.ones(960, device=DEV), torch.zeros(960, device=DEV), 32, 1e-5, True)
+
+
 @pytest.mark.parametrize("b,c,hw", [(26, 320, 32), (13, 128, 128), (5, 960, 32), (2, 2560, 4), (1, 64, 200)])
 def test_groupnorm_nhwc_many_chunks_and_reproducible(b, c, hw):
     """Shapes whose samples split into many pixel chunks (incl. > 16: the separate finalise pass, and ragged last chunks);
@@ -221,6 +261,28 @@ def test_geglu(inner):
     ref = a * F.gelu(gate)
     y = ops.geglu(x.to(DEV))
     assert (y.float().cpu() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("m,k,inner", [(1024 * 3, 320, 1280), (256 * 5, 640, 2560), (64 * 7 + 5, 1280, 5120), (16, 1280, 5120),
+                                        (1024 * 40, 320, 1280), (300, 72, 128)])
+def test_ff_geglu_gemm_vs_fp32(m, k, inner, dtype):
+    """Fused projection + GEGLU vs fp32 `h * gelu_erf(g)` on the same 16-bit operands (ragged M, K not a multiple of 64,
+    many tiles per persistent CTA), and vs the unfused library GEMM + dadd_geglu_fwd path it replaces."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(m + k + inner)
+    x = torch.randn(m, k, generator=g).to(dtype)
+    w = (torch.randn(2 * inner, k, generator=g) * (1.5 / math.sqrt(k))).to(dtype)
+    bias = 0.3 * torch.randn(2 * inner, generator=g)
+    rows = slice(0, m) if m <= 4096 else slice(m - 2048, m)            # the fp32 reference of the big case: its last rows
+    proj = F.linear(x[rows].float(), w.float(), bias)
+    ref = proj[:, :inner] * F.gelu(proj[:, inner:])
+    got = ops.ff_geglu(x.to(DEV), w.to(DEV), bias.to(DEV))
+    assert got.shape == (m, inner) and got.dtype == dtype
+    tol = 6e-3 if dtype == torch.bfloat16 else 1e-3
+    assert rel_err(got[rows], ref) <= tol, rel_err(got[rows], ref)
+    unfused = ops.geglu(F.linear(x.to(DEV), w.to(DEV), bias.to(DEV).to(dtype)))
+    assert rel_err(got, unfused.float()) <= 2 * tol
 
 
 # ------------------------------------------------------------------------------------------------ attention cores
@@ -315,6 +377,53 @@ def test_cross_attention_processors_vs_reference_golden(case, compute):
     assert rel_err(out, ref) <= (2e-2 if compute == torch.bfloat16 else 4e-3), rel_err(out, ref)
 
 
+def _cross_ref(q, k, v, gates, heads, seg, nseg):
+    """fp32: sum_s gates[s] softmax(q k_s^T / sqrt d) v_s on the 16-bit operands the kernels see."""
+    b, n, c = q.shape
+    d = c // heads
+    qh = q.float().view(b, n, heads, d).transpose(1, 2)
+    out = torch.zeros(b, heads, n, d)
+    for s in range(nseg):
+        ks, vs = k.float()[:, :, s * seg:(s + 1) * seg], v.float()[:, :, s * seg:(s + 1) * seg]
+        out += gates[s] * torch.softmax(qh @ ks.transpose(-1, -2) * d ** -0.5, dim=-1) @ vs
+    return out.transpose(1, 2).reshape(b, n, c)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("seg,nseg", [(16, 3), (16, 2), (32, 1)])
+@pytest.mark.parametrize("n,d,b", [(1024, 40, 3), (256, 80, 5), (128, 64, 2), (200, 40, 2), (4096, 40, 1), (333, 128, 1), (1024, 40, 40)])
+def test_cross_attention_core_tcgen05_vs_mma_vs_fp32(n, d, b, seg, nseg, dtype):
+    """The tcgen05 kernel (N >= 128), the mma.sync kernel and the fp32 reference on the same 16-bit operands; q is a strided
+    view (row stride 2C) as when it aliases a fused projection, and b = 40 gives every persistent CTA several items."""
+    ops = _ops()
+    heads, c = 8, 8 * d
+    g = torch.Generator().manual_seed(n + d + b + seg * nseg)
+    q = (1.5 * torch.randn(b, n, 2 * c, generator=g)).to(dtype)[:, :, c // 8: c // 8 + c]
+    k = (1.2 * torch.randn(b, heads, seg * nseg, d, generator=g)).to(dtype)
+    v = torch.randn(b, heads, seg * nseg, d, generator=g).to(dtype)
+    gates = torch.tensor([0.9, 0.1, 3.0][:nseg])
+    ref = _cross_ref(q, k, v, gates, heads, seg, nseg)
+    qd = torch.empty(b, n, 2 * c, dtype=dtype, device=DEV)[:, :, c // 8: c // 8 + c]
+    qd.copy_(q)
+    assert not qd.is_contiguous()
+    tc = ops.cross_attention(qd, k.to(DEV), v.to(DEV), gates.to(DEV), heads, seg, nseg, impl="tc")
+    mma = ops.cross_attention(qd, k.to(DEV), v.to(DEV), gates.to(DEV), heads, seg, nseg, impl="mma")
+    auto = ops.cross_attention(qd, k.to(DEV), v.to(DEV), gates.to(DEV), heads, seg, nseg)
+    tol = 1.2e-2 if dtype == torch.bfloat16 else 2e-3
+    assert rel_err(tc, ref) <= tol, rel_err(tc, ref)
+    assert rel_err(mma, ref) <= tol, rel_err(mma, ref)
+    assert torch.equal(auto, tc)                         # N >= 128, d <= 128 dispatches to the tcgen05 kernel, deterministically
+
+
+def test_cross_attention_tcgen05_rejects_unsupported_shapes():
+    ops = _ops()
+    from progressive_stable_diffusion_b200._lib import DaddError
+    q = torch.zeros(1, 64, 320, dtype=torch.bfloat16, device=DEV)
+    kv = torch.zeros(1, 8, 48, 40, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(DaddError):
+        ops.cross_attention(q, kv, kv, torch.ones(3, device=DEV), 8, 16, 3, impl="tc")      # N < 128
+
+
 def test_cross_attention_delta_zero_skips_pathway():
     """I2: delta_scale == 0 must equal a 2-segment launch regardless of what the delta tokens hold (even NaN)."""
     import progressive_stable_diffusion_b200 as P
@@ -363,6 +472,17 @@ def test_aoe_matches_reference_golden():
         # interpolation itself: table + gather + lerp, vs the oracle restatement
         interp = emb._interp(labels.to(DEV)).cpu()
         torch.testing.assert_close(interp, conditioning.aoe_interp(w, labels), atol=1e-7, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(3, 1280, 4, 4), (2, 640, 16, 16), (5, 128, 7, 9), (1, 8, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_upsample_nearest2x_bit_exact(shape, dtype):
+    ops = _ops()
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape))).to(dtype)
+    want = F.interpolate(x.float(), scale_factor=2.0, mode="nearest").to(dtype)
+    got = ops.upsample_nearest2x(x.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got.cpu(), want)
 
 
 def test_image_post():
