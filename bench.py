@@ -39,6 +39,15 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` at the bench batch, from the committed
+    ``ncu --set full`` capture summarised in profiles/ncu_traffic.json (None when that kernel has no capture yet)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -211,19 +220,38 @@ def run_b200(args) -> None:
         torch.cuda.synchronize(dev)
         attn_s = e0.elapsed_time(e1) / 1e3 / reps
         attn_flop = 4.0 * SELF_ATTN_N * SELF_ATTN_N * c * batch
-        # ---- GroupNorm+SiLU 320ch @32x32 (the most frequent memory-bound kernel) ----
-        xg = torch.randn(batch, 320, 32, 32, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        # ---- GroupNorm+SiLU 320ch @32x32 (the most frequent memory-bound kernel); a rotation of input/output pairs larger
+        # than the 126 MB L2 so that no launch finds its operands cached ----
+        nbuf = max(2, -(-(160 << 20) // (batch * 320 * 32 * 32 * 2 * 2)))
+        xgs = [torch.randn(batch, 320, 32, 32, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+               for _ in range(nbuf)]
+        ygs = [torch.empty_like(x) for x in xgs]
         gam, bet = torch.ones(320, device=dev), torch.zeros(320, device=dev)
-        for _ in range(3):
-            ops.group_norm(xg, gam, bet, 32, 1e-5, True)
+        for i in range(nbuf):
+            ops.group_norm(xgs[i], gam, bet, 32, 1e-5, True, out=ygs[i])
         torch.cuda.synchronize(dev)
         e0.record()
-        for _ in range(reps):
-            ops.group_norm(xg, gam, bet, 32, 1e-5, True)
+        for i in range(reps):
+            ops.group_norm(xgs[i % nbuf], gam, bet, 32, 1e-5, True, out=ygs[i % nbuf])
         e1.record()
         torch.cuda.synchronize(dev)
         gn_s = e0.elapsed_time(e1) / 1e3 / reps
-        gn_bytes = xg.numel() * 2 * 2
+        gn_bytes = xgs[0].numel() * 2 * 2
+        # ---- triple-pathway cross-attention N=1024, d=40 (tcgen05 kernel; HBM-bound: Q in + O out) ----
+        qx = [torch.randn(batch, SELF_ATTN_N, c, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+        kc = torch.randn(batch, SELF_ATTN_H, 48, SELF_ATTN_D, device=dev, dtype=torch.bfloat16)
+        vc = torch.randn(batch, SELF_ATTN_H, 48, SELF_ATTN_D, device=dev, dtype=torch.bfloat16)
+        gts = torch.tensor([0.9, 0.1, STEER], device=dev)
+        for i in range(3):
+            ops.cross_attention(qx[i], kc, vc, gts, SELF_ATTN_H, 16, 3)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for i in range(reps):
+            ops.cross_attention(qx[i % 3], kc, vc, gts, SELF_ATTN_H, 16, 3)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        xa_s = e0.elapsed_time(e1) / 1e3 / reps
+        xa_bytes = qx[0].numel() * 2 * 2 + kc.numel() * 2 * 2
 
     images_total = batch * world * args.steps
     value = images_total / seconds
@@ -253,11 +281,18 @@ def run_b200(args) -> None:
         "clocks": clocks,
         "roofline": {"kernel": "self_attn (N=1024, d=40, H=8) at the bench batch", "bound": "tensor",
                      "achieved": attn_flop / attn_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": attn_flop / attn_s / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
-                     "us_per_launch": attn_s * 1e6},
+                     "frac": attn_flop / attn_s / 1e12 / pk["bf16_tflops"], "traffic": ncu_traffic("self_attn"),
+                     "peak_source": pk["source"], "us_per_launch": attn_s * 1e6,
+                     "limiter": "MUFU.EX2 (16/clk/SM): 160 flop per exponential at d=40 caps the kernel at 744 TFLOP/s = 45 % "
+                                "of the tensor peak (profiles/r01_attn_poly_exp.txt)"},
         "roofline_groupnorm": {"kernel": "groupnorm+silu NHWC 320ch 32x32 at the bench batch", "bound": "hbm",
                                "achieved": gn_bytes / gn_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                               "frac": gn_bytes / gn_s / 1e9 / pk["hbm_gbs"], "traffic": None, "us_per_launch": gn_s * 1e6},
+                               "frac": gn_bytes / gn_s / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("groupnorm"),
+                               "us_per_launch": gn_s * 1e6},
+        "roofline_cross_attn": {"kernel": "triple-pathway cross_attn (N=1024, d=40, 48 tokens) at the bench batch", "bound": "hbm",
+                                "achieved": xa_bytes / xa_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                "frac": xa_bytes / xa_s / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("cross_attn"),
+                                "us_per_launch": xa_s * 1e6},
         "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
                                    f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},

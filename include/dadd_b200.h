@@ -122,6 +122,18 @@ int dadd_upsample_nearest2x_fwd(const void* x, void* y, int B, int H, int W, int
 /* GEGLU gate of the transformer feed-forward: y[r][j] = x[r][j] * gelu_erf(x[r][inner + j]), x: [rows][2*inner]. */
 int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream);
 
+/* Linear layer as a persistent tcgen05 GEMM with bias and residual add fused into its epilogue:
+ *   y[m][n] = sum_k x[m][k] w[n][k] (+ bias[n]) (+ residual[m][n])
+ * Replaces nn.Linear / 1x1-conv calls of diffusers' Transformer2DModel and BasicTransformerBlock (proj_in, to_q/to_k/to_v,
+ * to_out[0], ff.net[2], proj_out) and ResnetBlock2D.conv_shortcut reached through src/models/unet/unet.py:140-146, together
+ * with the residual adds that follow them (`ff(x) + x`, `proj_out(x) + residual`, `shortcut(x) + h`).
+ * x: [M][K], w: [N][K] (nn.Linear layout), y / residual: [M][N], all 16-bit `dtype`, dense rows, 16-byte aligned; bias: fp32 [N]
+ * (nullable); residual nullable and may alias y.  The product is rounded to 16 bits before the residual is added (as the
+ * unfused GEMM + add).  K % 8 == 0 and N a multiple of 160 or 256: dadd_linear_supported() says whether a shape qualifies. */
+int dadd_linear_supported(int64_t M, int N, int K);
+int dadd_linear_fwd(const void* x, const void* w, const float* bias /* nullable */, const void* residual /* nullable */, void* y,
+                    int64_t M, int N, int K, int dtype /* DADD_BF16 | DADD_F16 */, void* stream);
+
 /* Feed-forward input projection fused with the GEGLU gate (tcgen05 GEMM, GELU in the epilogue):
  *   y[m][j] = (x w[j]^T + bias[j]) * gelu_erf(x w[inner + j]^T + bias[inner + j]),  j < inner.
  * Replaces `hidden, gate = proj(x).chunk(2, -1); hidden * F.gelu(gate)` of diffusers' GEGLU (FeedForward.net[0] of every

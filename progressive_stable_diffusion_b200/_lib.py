@@ -27,6 +27,8 @@ SIGNATURES = {
     "dadd_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "dadd_bias_residual_fwd": [_P, _P, _P, _P, _L, _I, _I, _P],
     "dadd_upsample_nearest2x_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "dadd_linear_supported": [_L, _I, _I],
+    "dadd_linear_fwd": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "dadd_ff_geglu_fwd": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "dadd_geglu_fwd": [_P, _P, _L, _I, _I, _P],
     "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _P],

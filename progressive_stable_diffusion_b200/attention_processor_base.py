@@ -70,7 +70,7 @@ class OrdinalIPAttnProcessor2_0(nn.Module):
         x = x.to(compute_dtype())
         if not x.is_contiguous():
             x = x.contiguous()
-        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, compute_dtype()))
+        q = ops.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, compute_dtype()))
         k_cat, v_cat, length = self.project_kv(attn, encoder_hidden_states)
         one = wcache.get(self, "one", (attn.to_q.weight,), lambda: torch.ones(1, device=x.device, dtype=torch.float32))
         z = ops.cross_attention(q, k_cat, v_cat, one, attn.heads, length, 1)

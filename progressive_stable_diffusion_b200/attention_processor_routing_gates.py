@@ -122,7 +122,7 @@ class SplitInjectionAttentionProcessor(nn.Module):
         x = x.to(compute_dtype())
         if not x.is_contiguous():
             x = x.contiguous()
-        q = F.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, compute_dtype()))
+        q = ops.linear(x, wcache.cast(attn.to_q, "w", attn.to_q.weight, compute_dtype()))
         k_cat, v_cat, n_seg = self.project_kv(attn, encoder_hidden_states)
         z = ops.cross_attention(q, k_cat, v_cat, self.gate_vector(), attn.heads, self.num_aoe_tokens, n_seg)
         return _finish(attn, z, residual, shape4, out_dtype)

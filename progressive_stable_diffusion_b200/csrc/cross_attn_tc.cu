@@ -14,7 +14,7 @@
 //   * two softmax groups (warps 0-3 / 4-7) alternate over the items: tcgen05.ld of the L scores of the row, an independent
 //     softmax per SEG-token segment entirely in registers (no shuffles), the segment's routing gate folded into its
 //     normaliser (invariant I11: sum_s g_s P_s V_s = [g_s P_s]_s V_cat), 16-bit P back to TMEM, then the epilogue:
-//     O -> 16-bit -> 16-byte global stores from the row owner (heads merged, ready for to_out).
+//     O -> 16-bit -> (d <= 64) swizzled staging panel + one TMA store, (d > 64) 16-byte global stores from the row owner.
 // TMEM columns: S0 S1 [0,128) (P_q, 16-bit, overwrites S_q once the row owners hold the scores in registers), O0 O1 [128, 128 +
 // 128 NP): 256 columns for d <= 64, so TWO CTAs share an SM there (the per-item chain QK -> softmax -> PV -> epilogue is latency-
 // bound; four row groups per SM in flight hide it), 384 -> one CTA for d <= 128.
@@ -42,6 +42,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -53,7 +59,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 template <typename T, int NP, int SEG, int NSEG, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, NP == 1 ? 2 : 1)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                     const __grid_constant__ CUtensorMap tv, T* __restrict__ o, int64_t o_stride, int B, int H, int N, int d,
+                     const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, T* __restrict__ o,
+                     int64_t o_stride, int B, int H, int N, int d,
                      const float* __restrict__ gates, float scale_log2e) {
     constexpr int L = SEG * NSEG;
     constexpr uint32_t TMEM_COLS = NP == 1 ? 256 : 512;
@@ -70,7 +77,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sStage = smem;                                // [STAGES]{Q[NP], K[NP], V[NP]}
-    Bars<STAGES>* bars = reinterpret_cast<Bars<STAGES>*>(sStage + STAGES * STAGE_BYTES);
+    // d <= 64: a head's output row is 80 .. 128 bytes that straddle 128-byte lines, so it leaves through a swizzled staging
+    // panel and one TMA store (1.75 L2 requests per row instead of one 16-byte request per chunk); wider heads store directly
+    constexpr bool TMA_STORE = NP == 1;
+    unsigned char* sO = sStage + STAGES * STAGE_BYTES;           // [2 groups] staging panel (TMA_STORE only)
+    Bars<STAGES>* bars = reinterpret_cast<Bars<STAGES>*>(sO + (TMA_STORE ? 2 * Q_PANEL : 0));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nq = (N + BM - 1) / BM;
@@ -167,6 +178,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         const uint32_t tS = tmem + COL_S + q * 64 + lane_base;
         const uint32_t tP = tS;
         const uint32_t tO = tmem + COL_O + q * (64 * NP) + lane_base;
+        const bool store_leader = (warp & 3) == 0 && lane == 0;
         float gate[NSEG];
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) gate[s] = gates[s];
@@ -212,33 +224,63 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
             tmem_wait_st();
             fence_before();
             mbar_arrive(&bars->p_full[q]);
-            // epilogue: O -> 16-bit -> global, 16 bytes per store straight from the row owner's registers (a row of one head is
-            // d * 2 <= 256 contiguous bytes; the partially written 32-byte sectors at its ends are completed in L2 by the
-            // neighbouring heads' CTAs).  No staging panel: shared memory goes to the load ring instead.
+            // epilogue: O -> 16-bit -> global (heads merged, ready for to_out)
             mbar_wait(&bars->o_full[q], k & 1);
             fence_after();
-            const int grow = t * BM + wrow;
-            T* orow = o + ((int64_t)b * N + grow) * o_stride + (int64_t)h * d;
             const int chunks = d >> 3;
+            if constexpr (TMA_STORE) {
+                if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has left the panel
+                named_sync(1 + q, 128);
+                unsigned char* stage = sO + q * Q_PANEL + wrow * 128;
 #pragma unroll 1
-            for (int c0 = 0; c0 < chunks; c0 += 4) {
-                uint32_t r[32];
-                tmem_ld32(tO + c0 * 8, r);
-                tmem_wait_ld();
+                for (int c0 = 0; c0 < chunks; c0 += 4) {
+                    uint32_t r[32];
+                    tmem_ld32(tO + c0 * 8, r);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    if (c0 + cc < chunks && grow < N) {
-                        uint4 out;
-                        out.x = pack2<T>(__uint_as_float(r[cc * 8 + 0]), __uint_as_float(r[cc * 8 + 1]));
-                        out.y = pack2<T>(__uint_as_float(r[cc * 8 + 2]), __uint_as_float(r[cc * 8 + 3]));
-                        out.z = pack2<T>(__uint_as_float(r[cc * 8 + 4]), __uint_as_float(r[cc * 8 + 5]));
-                        out.w = pack2<T>(__uint_as_float(r[cc * 8 + 6]), __uint_as_float(r[cc * 8 + 7]));
-                        *reinterpret_cast<uint4*>(orow + (c0 + cc) * 8) = out;
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int c = c0 + cc;
+                        if (c < chunks) {
+                            uint4 out;
+                            out.x = pack2<T>(__uint_as_float(r[cc * 8 + 0]), __uint_as_float(r[cc * 8 + 1]));
+                            out.y = pack2<T>(__uint_as_float(r[cc * 8 + 2]), __uint_as_float(r[cc * 8 + 3]));
+                            out.z = pack2<T>(__uint_as_float(r[cc * 8 + 4]), __uint_as_float(r[cc * 8 + 5]));
+                            out.w = pack2<T>(__uint_as_float(r[cc * 8 + 6]), __uint_as_float(r[cc * 8 + 7]));
+                            *reinterpret_cast<uint4*>(stage + (((c & 7) ^ (wrow & 7)) << 4)) = out;   // 128-byte swizzle
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                fence_before();
+                named_sync(1 + q, 128);
+                if (store_leader) {
+                    tma_store_4d(&to, smem_u32(sO + q * Q_PANEL), 0, t * BM, h, b);      // rows >= N, columns >= d clipped by TMA
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
+                const int grow = t * BM + wrow;
+                T* orow = o + ((int64_t)b * N + grow) * o_stride + (int64_t)h * d;
+#pragma unroll 1
+                for (int c0 = 0; c0 < chunks; c0 += 4) {
+                    uint32_t r[32];
+                    tmem_ld32(tO + c0 * 8, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        if (c0 + cc < chunks && grow < N) {
+                            uint4 out;
+                            out.x = pack2<T>(__uint_as_float(r[cc * 8 + 0]), __uint_as_float(r[cc * 8 + 1]));
+                            out.y = pack2<T>(__uint_as_float(r[cc * 8 + 2]), __uint_as_float(r[cc * 8 + 3]));
+                            out.z = pack2<T>(__uint_as_float(r[cc * 8 + 4]), __uint_as_float(r[cc * 8 + 5]));
+                            out.w = pack2<T>(__uint_as_float(r[cc * 8 + 6]), __uint_as_float(r[cc * 8 + 7]));
+                            *reinterpret_cast<uint4*>(orow + (c0 + cc) * 8) = out;
+                        }
                     }
                 }
             }
             fence_before();      // the O reads are ordered before this group's next P arrive (-> the next PV overwrites O)
         }
+        if (TMA_STORE && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     fence_before();
     __syncthreads();
@@ -265,16 +307,16 @@ static int make_map_strided(CUtensorMap* map, const void* base, int64_t row_stri
 }
 
 template <typename T, int NP, int SEG, int NSEG, int STAGES>
-static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, int64_t o_stride, int B, int H, int N,
-                  int d, const float* gates, float scale, cudaStream_t s) {
+static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, void* o, int64_t o_stride,
+                  int B, int H, int N, int d, const float* gates, float scale, cudaStream_t s) {
     constexpr int L = SEG * NSEG;
-    const size_t smem = (size_t)STAGES * NP * (128 * 128 + 2 * L * 128) + sizeof(Bars<STAGES>) + 1024;
+    const size_t smem = (size_t)STAGES * NP * (128 * 128 + 2 * L * 128) + (NP == 1 ? 2 * 128 * 128 : 0) + sizeof(Bars<STAGES>) + 1024;
     const int items = ((N + BM - 1) / BM) * H * B;
     const int ctas = (NP == 1 ? 2 : 1) * num_sms();
     const int grid = items < ctas ? items : ctas;
     auto kern = cross_attn_tc_kernel<T, NP, SEG, NSEG, STAGES>;
     if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cross_attn_tc smem")) return 2;
-    kern<<<grid, NTHREADS, smem, s>>>(tq, tk, tv, (T*)o, o_stride, B, H, N, d, gates, scale * 1.4426950408889634f);
+    kern<<<grid, NTHREADS, smem, s>>>(tq, tk, tv, to, (T*)o, o_stride, B, H, N, d, gates, scale * 1.4426950408889634f);
     return launched("dadd_cross_attn_fwd(tcgen05)");
 }
 
@@ -287,18 +329,18 @@ bool cross_attn_tc_supported(int N, int d, int seg_len, int n_seg) {
 int cross_attn_tc(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, void* o, int64_t o_stride, int B, int H,
                   int N, int d, int seg_len, int n_seg, const float* gates, float scale, int dtype, cudaStream_t s) {
     const int L = seg_len * n_seg;
-    CUtensorMap tq, tk, tv;
-    if (tc::make_map(&tq, q, q_stride, B, H, N, d, dtype, 128) ||
+    CUtensorMap tq, tk, tv, to;
+    if (tc::make_map(&tq, q, q_stride, B, H, N, d, dtype, 128) || tc::make_map(&to, o, o_stride, B, H, N, d, dtype, 128) ||
         xtc::make_map_strided(&tk, k_cat, d, (int64_t)L * d, (int64_t)H * L * d, B, H, L, d, dtype, L) ||
         xtc::make_map_strided(&tv, v_cat, d, (int64_t)L * d, (int64_t)H * L * d, B, H, L, d, dtype, L))
         return 1;
     const int np = (d + 63) / 64;
 #define DADD_XTC(NPV, SEGV, NSEGV, STG) \
-    DADD_DISPATCH_16(dtype, T, return (xtc::launch<T, NPV, SEGV, NSEGV, STG>(tq, tk, tv, o, o_stride, B, H, N, d, gates, scale, s)))
+    DADD_DISPATCH_16(dtype, T, return (xtc::launch<T, NPV, SEGV, NSEGV, STG>(tq, tk, tv, to, o, o_stride, B, H, N, d, gates, scale, s)))
     if (np == 1) {
-        if (n_seg == 3) DADD_XTC(1, 16, 3, 3);
-        if (n_seg == 2) DADD_XTC(1, 16, 2, 3);
-        DADD_XTC(1, 32, 1, 3);
+        if (n_seg == 3) DADD_XTC(1, 16, 3, 2);
+        if (n_seg == 2) DADD_XTC(1, 16, 2, 2);
+        DADD_XTC(1, 32, 1, 2);
     }
     if (n_seg == 3) DADD_XTC(2, 16, 3, 3);
     if (n_seg == 2) DADD_XTC(2, 16, 2, 3);

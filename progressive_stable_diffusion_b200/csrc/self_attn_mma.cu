@@ -7,6 +7,18 @@
 
 namespace daddk {
 
+// 16-byte global -> shared copy that does not pass through registers; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void sa_cp_async16(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+// B fragment (16 keys x 8 columns) of a row-major [key][column] tile: ldmatrix with transpose
+__device__ __forceinline__ void sa_load_b_frag_trans(uint32_t& b0, uint32_t& b1, const void* row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(b0), "=r"(b1)
+                 : "r"((uint32_t)__cvta_generic_to_shared(row_ptr)));
+}
+
 template <typename T, int DK>
 __global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict__ q,
                                                             const T* __restrict__ k,
@@ -15,11 +27,10 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict_
                                                             T* __restrict__ o, int64_t o_stride, int N,
                                                             int d, float scale_log2e) {
     constexpr int QS = DK + 8;
-    constexpr int VS = 64 + 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Qs = reinterpret_cast<T*>(smem_raw);   // [64][QS]
     T* Ks = Qs + 64 * QS;                                  // [64][QS]
-    T* Vt = Ks + 64 * QS;                                  // [DK][VS]
+    T* Vs = Ks + 64 * QS;                                  // [64][QS]  (row-major; PV reads it through ldmatrix.trans)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -34,9 +45,8 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict_
 
     for (int i = tid; i < 64 * DKV; i += 128) {
         const int r = i / DKV, c = i % DKV;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (c < dv && row0 + r < N) val = *reinterpret_cast<const uint4*>(qb + (int64_t)r * q_stride + c * 8);
-        *reinterpret_cast<uint4*>(Qs + r * QS + c * 8) = val;
+        const bool ok = c < dv && row0 + r < N;
+        sa_cp_async16(Qs + r * QS + c * 8, ok ? qb + (int64_t)r * q_stride + c * 8 : q, ok ? 16 : 0);
     }
 
     float acc[DK / 8][4];
@@ -47,20 +57,13 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict_
     const T* qw = Qs + (warp * 16) * QS;
     for (int kv0 = 0; kv0 < N; kv0 += 64) {
         __syncthreads();   // previous tile fully consumed (also orders the Q fill before first use)
-        for (int i = tid; i < 64 * DKV; i += 128) {
+        for (int i = tid; i < 64 * DKV; i += 128) {       // one global round trip for the whole K / V tile (and Q the first time)
             const int r = i / DKV, c = i % DKV;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (c < dv && kv0 + r < N) val = *reinterpret_cast<const uint4*>(kb + (int64_t)(kv0 + r) * k_stride + c * 8);
-            *reinterpret_cast<uint4*>(Ks + r * QS + c * 8) = val;
+            const bool ok = c < dv && kv0 + r < N;
+            sa_cp_async16(Ks + r * QS + c * 8, ok ? kb + (int64_t)(kv0 + r) * k_stride + c * 8 : k, ok ? 16 : 0);
+            sa_cp_async16(Vs + r * QS + c * 8, ok ? vb + (int64_t)(kv0 + r) * v_stride + c * 8 : v, ok ? 16 : 0);
         }
-        for (int i = tid; i < 64 * dv; i += 128) {
-            const int r = i / dv, c = i % dv;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (kv0 + r < N) val = *reinterpret_cast<const uint4*>(vb + (int64_t)(kv0 + r) * v_stride + c * 8);
-            const T* e = reinterpret_cast<const T*>(&val);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) Vt[(c * 8 + j) * VS + r] = e[j];
-        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
         float s[8][4];
@@ -120,8 +123,8 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict_
 #pragma unroll
             for (int nd = 0; nd < DK / 8; ++nd) {
                 if (nd < dv) {
-                    uint32_t b0, b1;
-                    load_b_frag(b0, b1, Vt + (nd * 8) * VS, VS, kk * 16, g, t);
+                    uint32_t b0, b1;      // lanes 0-15 address the 16 key rows of this k-step, 8 columns wide
+                    sa_load_b_frag_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * QS + nd * 8);
                     mma_16816<T>(acc[nd], a, b0, b1);
                 }
             }
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) self_attn_mma_kernel(const T* __restrict_
 template <typename T, int DK>
 static int launch_self_mma(const void* q, const void* k, const void* v, int64_t qs, int64_t ks, int64_t vs, void* o,
                            int64_t os, int B, int H, int N, int d, float scale, cudaStream_t s) {
-    const size_t smem = ((size_t)64 * (DK + 8) * 2 + (size_t)DK * 72) * sizeof(T);
+    const size_t smem = (size_t)3 * 64 * (DK + 8) * sizeof(T);
     auto kern = self_attn_mma_kernel<T, DK>;
     if (smem > 48 * 1024) {
         if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "self_attn smem"))

@@ -208,6 +208,59 @@ def geglu(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+# Which GEMM ``linear(..., impl="auto")`` runs: "lib" = cuBLAS (+ one fused bias / residual pass), "tc" = dadd_linear_fwd where
+# the shape qualifies.  Measured on B200 (profiles/r01_linear_gemm.txt): the one-CTA 128 x 160/256 tiles of dadd_linear_fwd
+# re-read their operands from L2 too often and lose 10-25 % to cuBLAS' two-CTA 256-wide tiles, so the default is "lib".
+LINEAR_IMPL = "lib"
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, impl: str = "auto") -> torch.Tensor:
+    """``F.linear(x, w, bias) (+ residual)``: x (..., K) 16-bit, w (N, K) same dtype, bias (N,) fp32, residual (..., N).
+    ``impl``: "tc" = the tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``; K % 8 == 0, N a multiple of
+    160 or 256, dense operands), "lib" = library GEMM followed by the fused bias / residual pass, "auto" = ``LINEAR_IMPL``."""
+    _cuda(x, w, bias, residual)
+    k, n = x.shape[-1], w.shape[0]
+    m = x.numel() // k
+    assert w.shape == (n, k) and w.dtype == x.dtype and x.dtype in (torch.bfloat16, torch.float16)
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() == n)
+    shape = (*x.shape[:-1], n)
+    lib = _lib.load()
+    impl = LINEAR_IMPL if impl == "auto" else impl
+    tc_ok = bool(lib.dadd_linear_supported(m, n, k)) and x.is_contiguous() and w.is_contiguous() and (residual is None or residual.is_contiguous())
+    if impl == "tc" and not tc_ok:
+        raise _lib.DaddError(f"dadd_linear_fwd does not take M={m} N={n} K={k} (or an operand is not dense)")
+    if impl == "tc":
+        y = torch.empty(shape, dtype=x.dtype, device=x.device) if out is None else out
+        assert y.is_contiguous() and y.shape == shape and (residual is None or residual.shape == shape)
+        _lib.check(lib.dadd_linear_fwd(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), m, n, k, _dt(x),
+                                       _stream()), "dadd_linear_fwd")
+        return y
+    if residual is None:                               # bias in the library GEMM's own epilogue
+        y = torch.nn.functional.linear(x, w, None if bias is None else _bias16(bias, x.dtype))
+        if out is not None:
+            out.copy_(y)
+            y = out
+        return y
+    y = torch.nn.functional.linear(x, w)
+    return bias_residual(y, residual, bias, out=y if out is None else out)
+
+
+_BIAS16 = {}
+
+
+def _bias16(bias: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """16-bit copy of an fp32 bias for the library GEMM epilogue (address-stable, rebuilt when the source changes)."""
+    key = (bias.data_ptr(), dtype)
+    hit = _BIAS16.get(key)
+    if hit is None or hit[0] != bias._version or hit[1].numel() != bias.numel():
+        if len(_BIAS16) > 4096:
+            _BIAS16.clear()
+        hit = (bias._version, bias.detach().to(dtype))
+        _BIAS16[key] = hit
+    return hit[1]
+
+
 def ff_geglu(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``h, g = F.linear(x, w, bias).chunk(2, -1); h * gelu(g)`` as one tcgen05 GEMM with the gate in its epilogue.
     x (..., K) 16-bit contiguous, w (2*inner, K) same dtype, bias (2*inner,) fp32 -> (..., inner)."""

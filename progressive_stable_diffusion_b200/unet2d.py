@@ -54,10 +54,9 @@ def _conv(mod: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     return y + wcache.cast(mod, "b", mod.bias, compute_dtype()).view(1, -1, 1, 1)
 
 
-def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
-    w = wcache.cast(mod, "w", mod.weight, compute_dtype())
-    b = None if mod.bias is None else wcache.cast(mod, "b", mod.bias, compute_dtype())
-    return F.linear(x, w, b)
+def _linear(mod: nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``mod(x) (+ residual)``: tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``)."""
+    return ops.linear(x, wcache.cast(mod, "w", mod.weight, compute_dtype()), _bias32(mod), residual)
 
 
 def _conv1x1_weight(mod: nn.Conv2d, cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
@@ -70,16 +69,20 @@ def _conv1x1_weight(mod: nn.Conv2d, cols: Optional[Tuple[int, int]] = None) -> t
 
 
 def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor, extra_bias: Optional[nn.Module] = None,
-                       cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-    """1x1 convolution as a GEMM on channels-last tokens (bias in the GEMM epilogue).  ``extra_bias``: a module whose bias
-    is added on top (a resnet's conv2 bias rides on its shortcut GEMM).  ``cols``: use only these input channels."""
+                       cols: Optional[Tuple[int, int]] = None, residual: Optional[torch.Tensor] = None,
+                       bias: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1 convolution as a GEMM on channels-last tokens, bias and ``residual`` (tokens) in the GEMM epilogue.
+    ``extra_bias``: a module whose bias is added on top (a resnet's conv2 bias rides on its shortcut GEMM).  ``cols``: use
+    only these input channels.  ``bias=False`` leaves the bias out (second half of a split GEMM)."""
     w = _conv1x1_weight(mod, cols)
-    if extra_bias is None:
-        b = wcache.cast(mod, "b", mod.bias, compute_dtype())
+    if not bias:
+        b = None
+    elif extra_bias is None:
+        b = _bias32(mod)
     else:
-        b = wcache.get(mod, "b+", (mod.bias, extra_bias.bias),
-                       lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).to(compute_dtype()).contiguous())
-    return F.linear(tokens, w, b)
+        b = wcache.get(mod, "b32+", (mod.bias, extra_bias.bias),
+                       lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).contiguous())
+    return ops.linear(tokens, w, b, residual, out=out)
 
 
 def _tokens(x: torch.Tensor) -> torch.Tensor:
@@ -162,7 +165,8 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        # ``net(x) (+ residual)``: the residual add of the transformer block rides on the output GEMM's epilogue
         # (slicing the batch so that proj -> GEGLU -> out stays inside L2 was measured slower than one pass: the smaller
         # GEMMs lose more than the L2-resident intermediate gains; profiles/r01_ff_slice_ab.txt)
         proj = self.net[0].proj
@@ -170,7 +174,7 @@ class FeedForward(nn.Module):
             g = ops.ff_geglu(x, wcache.cast(proj, "w", proj.weight, compute_dtype()), _bias32(proj))
         else:
             g = ops.geglu(_linear(proj, x))
-        return _linear(self.net[2], g)
+        return _linear(self.net[2], g, residual)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -185,10 +189,10 @@ class BasicTransformerBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
         # hidden = attn(norm(hidden)) + hidden, three times; each residual add is fused with the
-        # LayerNorm that follows it, the last one is a plain vectorised add
+        # LayerNorm that follows it, the last one with the feed-forward's output GEMM
         x, n = _add_ln(self.norm2, x, self.attn1(_ln(self.norm1, x)))
         x, n = _add_ln(self.norm3, x, self.attn2(n, encoder_hidden_states=ehs))
-        return ops.bias_residual(self.ff(n), x)
+        return self.ff(n, residual=x)
 
 
 class Transformer2DModel(nn.Module):
@@ -207,8 +211,7 @@ class Transformer2DModel(nn.Module):
         t = _conv1x1_as_linear(self.proj_in, t)
         for blk in self.transformer_blocks:
             t = blk(t, ehs)
-        t = _conv1x1_as_linear(self.proj_out, t)
-        return _image(ops.bias_residual(t, _tokens(x)), h, w)
+        return _image(_conv1x1_as_linear(self.proj_out, t, residual=_tokens(x)), h, w)
 
 
 class ResnetBlock2D(nn.Module):
@@ -244,14 +247,16 @@ class ResnetBlock2D(nn.Module):
         h = _conv_nobias(self.conv2, _gn(self.norm2, h, silu=True, chan_add=temb_term))
         if self.conv_shortcut is None:
             return ops.bias_residual(h, x, _bias32(self.conv2), out=h)
+        # out = shortcut(x) + conv2(h) + both biases: the 1x1 shortcut GEMM takes h as the residual of its epilogue; with a
+        # skip tensor it is two accumulating GEMMs over the two halves of its weight (the second adds onto the first in place)
         b, c1, hh, ww = x.shape
         if skip is None:
-            sc = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2)
+            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2, residual=_tokens(h))
         else:
-            sc = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2, cols=(0, c1))
-            w2 = _conv1x1_weight(self.conv_shortcut, (c1, c1 + skip.shape[1]))
-            sc.view(-1, sc.shape[-1]).addmm_(_tokens(skip).reshape(-1, skip.shape[1]), w2.t())
-        return ops.bias_residual(h, _image(sc, hh, ww), out=h)
+            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2, cols=(0, c1), residual=_tokens(h))
+            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(skip), cols=(c1, c1 + skip.shape[1]), residual=out, bias=False,
+                                     out=out)
+        return _image(out, hh, ww)
 
 
 class Downsample2D(nn.Module):

@@ -165,6 +165,25 @@ if on("ff1"):
         us, mn = timeit(lambda: ops.ff_geglu(x, w, b32))
         report(f"ff1 fused tcgen05 N={N} C={C} B={B}", us, mn, flops=flops)
 
+if on("lin"):
+    import torch.nn.functional as F
+    for C, N in sites:
+        x = torch.randn(B, N, C, device=dev, dtype=dt)
+        h = torch.randn(B, N, 4 * C, device=dev, dtype=dt)
+        r = torch.randn(B, N, C, device=dev, dtype=dt)
+        for name, inp, nout, kin, use_res in (("qkv", x, 3 * C, C, False), ("proj", x, C, C, False), ("ff2+res", h, C, 4 * C, True)):
+            w = torch.randn(nout, kin, device=dev, dtype=dt) * (kin ** -0.5)
+            b32 = torch.randn(nout, device=dev)
+            b16 = b32.to(dt)
+            flops = 2.0 * B * N * kin * nout
+            if use_res:
+                us, mn = timeit(lambda: ops.bias_residual(F.linear(inp, w, b16), r))
+            else:
+                us, mn = timeit(lambda: F.linear(inp, w, b16))
+            report(f"{name} library N={N} C={C} B={B}", us, mn, flops=flops)
+            us, mn = timeit(lambda: ops.linear(inp, w, b32, r if use_res else None, impl="tc"))
+            report(f"{name} tcgen05 N={N} C={C} B={B}", us, mn, flops=flops)
+
 if on("add_ln"):
     for C, N in sites:
         x = torch.randn(B, N, C, device=dev, dtype=dt)

@@ -285,6 +285,48 @@ def test_ff_geglu_gemm_vs_fp32(m, k, inner, dtype):
     assert rel_err(got, unfused.float()) <= 2 * tol
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("m,n,k", [(1024 * 3, 320, 320), (256 * 5, 640, 640), (64 * 7 + 5, 1280, 1280), (16, 1280, 1280),
+                                    (1024 * 40, 960, 320), (2048, 320, 1280), (300, 160, 72), (1664, 3840, 1280), (777, 1920, 640),
+                                    (129, 512, 512)])
+def test_linear_gemm_bias_residual_vs_fp32(m, n, k, dtype):
+    """dadd_linear_fwd (both tile widths, ragged M, K not a multiple of 64, many tiles per CTA) with every bias / residual
+    combination vs fp32 on the same 16-bit operands; the residual may alias the output."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).to(dtype)
+    w = (torch.randn(n, k, generator=g) * (1.5 / math.sqrt(k))).to(dtype)
+    bias = 0.3 * torch.randn(n, generator=g)
+    res = torch.randn(m, n, generator=g).to(dtype)
+    rows = slice(0, m) if m <= 4096 else slice(m - 2048, m)
+    base = F.linear(x[rows].float(), w.float())
+    xd, wd, bd, rd = x.to(DEV), w.to(DEV), bias.to(DEV), res.to(DEV)
+    tol = 6e-3 if dtype == torch.bfloat16 else 1e-3
+    for use_bias, use_res in ((False, False), (True, False), (False, True), (True, True)):
+        ref = base + (bias if use_bias else 0) + (res[rows].float() if use_res else 0)
+        got = ops.linear(xd, wd, bd if use_bias else None, rd if use_res else None, impl="tc")
+        assert got.shape == (m, n) and got.dtype == dtype
+        lib = ops.linear(xd, wd, bd if use_bias else None, rd if use_res else None, impl="lib")
+        assert rel_err(lib[rows], ref) <= tol
+        assert rel_err(got[rows], ref) <= tol, (use_bias, use_res, rel_err(got[rows], ref))
+    inplace = rd.clone()
+    ops.linear(xd, wd, bd, inplace, out=inplace, impl="tc")
+    assert torch.equal(inplace, got)
+
+
+def test_linear_library_path_for_other_widths():
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x, w = torch.randn(100, 64, generator=g).to(torch.bfloat16), torch.randn(24, 64, generator=g).to(torch.bfloat16)
+    bias, res = torch.randn(24, generator=g), torch.randn(100, 24, generator=g).to(torch.bfloat16)
+    got = ops.linear(x.to(DEV), w.to(DEV), bias.to(DEV), res.to(DEV))
+    ref = F.linear(x.float(), w.float(), bias) + res.float()
+    assert rel_err(got, ref) <= 1e-2
+    from progressive_stable_diffusion_b200._lib import DaddError
+    with pytest.raises(DaddError):
+        ops.linear(x.to(DEV), w.to(DEV), bias.to(DEV), res.to(DEV), impl="tc")
+
+
 # ------------------------------------------------------------------------------------------------ attention cores
 SELF_SHAPES = [(1024, 40, 2), (256, 80, 2), (64, 160, 3), (16, 160, 2), (100, 40, 1), (4096, 40, 1), (200, 64, 1),
                (130, 128, 1), (256, 160, 2), (1024, 80, 1), (128, 40, 3), (384, 72, 1)]
