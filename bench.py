@@ -205,7 +205,9 @@ def run_b200(args) -> None:
         seconds_e2e = timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None
 
-        # ---- dominant kernel, timed live on the launching stream: self-attention N=1024, d=40 at this batch ----
+        # ---- dominant kernel, timed live on the launching stream: self-attention N=1024, d=40 at this batch (a kernel timed
+        # alone, after a pause that lets the power-capped clocks of the long step recover: the burst peaks are its roofline) ----
+        time.sleep(3.0)
         c = SELF_ATTN_H * SELF_ATTN_D
         qkv = torch.randn(batch, SELF_ATTN_N, 3 * c, device=dev, dtype=torch.bfloat16)
         reps = 20
@@ -252,6 +254,16 @@ def run_b200(args) -> None:
         torch.cuda.synchronize(dev)
         xa_s = e0.elapsed_time(e1) / 1e3 / reps
         xa_bytes = qx[0].numel() * 2 * 2 + kc.numel() * 2 * 2
+
+        if args.profile_step:      # one eager denoising step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+            eng.state.zero_()
+            eng._step()
+            torch.cuda.synchronize(dev)
+            eng.state.zero_()
+            torch.cuda.profiler.start()
+            eng._step()
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.stop()
 
     images_total = batch * world * args.steps
     value = images_total / seconds
@@ -306,6 +318,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--patients", type=int, default=8, help="patient progressions per GPU per step (13 images each)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the timed region run ONE eager denoising step inside cudaProfilerStart/Stop (for the ncu launch list)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

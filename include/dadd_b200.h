@@ -28,7 +28,7 @@ extern "C" {
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
 
-/* ABI version of this header (bumped on any signature change; currently 5). */
+/* ABI version of this header (bumped on any signature change; currently 6). */
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -72,10 +72,10 @@ int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64
  *   y = act(GroupNorm_G(x + chan_add[b * chan_add_stride + c]; eps) * gamma[c] + beta[c]),  act = SiLU or identity.
  * Statistics in fp32 (shifted sums + Chan combine).  x/y: `dtype`; gamma/beta/chan_add: fp32.
  * C % G == 0 and C % 8 == 0 required; for NHWC additionally (C/8) <= 512.
- * NHWC: samples up to ~1.5 MB with >= 8 channels per group (every UNet site) run as ONE launch - a thread-block cluster
- * per sample stages its slab in shared memory and combines statistics through distributed shared memory; larger
- * samples (the VAE decoder) run as flat passes (partial statistics per pixel chunk, finalise, normalise; the second read
- * of x comes from L2).  Callers always pass `workspace`: at least dadd_groupnorm_workspace_bytes(B, C, HW, G, layout) bytes of device memory,
+ * NHWC: samples up to ~2.3 MB with >= 8 channels per group (every 256x256 UNet site) run as ONE launch - a thread-block
+ * cluster per sample stages its slab in shared memory and combines statistics through distributed shared memory; larger
+ * samples (512x512 latents, the VAE decoder) run as flat passes (partial statistics per pixel chunk, then normalise with
+ * the group statistics finalised per CTA or, for many chunks, by a per-sample pass; the second read of x comes from L2).  Callers always pass `workspace`: at least dadd_groupnorm_workspace_bytes(B, C, HW, G, layout) bytes of device memory,
  * 16-byte aligned, borrowed until the queued work has run.  NCHW needs none (0 bytes, NULL allowed).
  */
 int64_t dadd_groupnorm_workspace_bytes(int B, int C, int HW, int G, int layout);
@@ -86,13 +86,14 @@ int dadd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, con
 /* GroupNorm of a channel concatenation that is never materialised: the input is [x1 | x2] along channels (the
  * `torch.cat([hidden, skip], dim=1)` feeding every resnet of the up path, diffusers UpBlock2D / CrossAttnUpBlock2D reached
  * through src/models/unet/unet.py:140-146); y is the normalised concatenation [B][HW][C1 + C2], NHWC, 16-bit `dtype`.
- * x1: [B][HW][C1], x2: [B][HW][C2]; C1 % 8 == 0, C2 % 8 == 0, (C1 + C2) % G == 0.  Runs only as the one-launch cluster
- * kernel: dadd_groupnorm_cat_supported() says whether a shape qualifies (every 256x256 UNet site does); otherwise the
- * call fails and the caller concatenates. */
+ * x1: [B][HW][C1], x2: [B][HW][C2]; C1 % 8 == 0, C2 % 8 == 0, (C1 + C2) % G == 0, (C1 + C2) / 8 <= 512
+ * (dadd_groupnorm_cat_supported()).  Same kernels, path selection and workspace rule as dadd_groupnorm_fwd(NHWC) with
+ * C = C1 + C2: workspace >= dadd_groupnorm_workspace_bytes(B, C1 + C2, HW, G, DADD_LAYOUT_NHWC). */
 int dadd_groupnorm_cat_supported(int B, int C1, int C2, int HW, int G, int dtype);
 int dadd_groupnorm_cat_fwd(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
                            const float* chan_add /* nullable */, int64_t chan_add_stride, void* y, int B, int HW, int G,
-                           float eps, int apply_silu, int dtype /* DADD_BF16 | DADD_F16 */, void* stream);
+                           float eps, int apply_silu, int dtype /* DADD_BF16 | DADD_F16 */, void* workspace,
+                           int64_t workspace_bytes, void* stream);
 
 /* LayerNorm over the last dimension (the 48 LayerNorms of the BasicTransformerBlocks and the three of
  * src/models/feature_purifier.py:46-47,62).  x,y: [rows][C] `dtype`; gamma/beta fp32; C % 8 == 0, C <= 2048. */

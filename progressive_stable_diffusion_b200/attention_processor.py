@@ -54,8 +54,9 @@ def _finish(attn, out: torch.Tensor, residual: torch.Tensor, shape4, out_dtype: 
     """to_out[0] (+bias), to_out[1] = Dropout(0), optional reshape / residual / rescale (routing_gates.py:183-196)."""
     w = wcache.cast(attn.to_out[0], "w", attn.to_out[0].weight, compute_dtype())
     bias = attn.to_out[0].bias
-    bias = None if bias is None else wcache.cast(attn.to_out[0], "b32", bias, torch.float32)
-    out = ops.linear(out, w, bias)
+    b32 = None if bias is None else wcache.cast(attn.to_out[0], "b32", bias, torch.float32)
+    b_lp = None if bias is None else wcache.cast(attn.to_out[0], "b", bias, compute_dtype())
+    out = ops.linear(out, w, b32, bias_lp=b_lp)
     if shape4 is not None:
         b, c, h, w_ = shape4
         out = out.transpose(-1, -2).reshape(b, c, h, w_)
@@ -92,11 +93,12 @@ class AttnProcessor2_0:
                           lambda: torch.cat([attn.to_q.weight, attn.to_k.weight, attn.to_v.weight], 0)
                           .detach().to(compute_dtype()).contiguous())
         c = attn.to_q.weight.shape[0]
-        bqkv = None
+        bqkv = bqkv_lp = None
         if attn.to_q.bias is not None:
             bqkv = wcache.get(attn, "bqkv32", (attn.to_q.bias, attn.to_k.bias, attn.to_v.bias),
                               lambda: torch.cat([attn.to_q.bias, attn.to_k.bias, attn.to_v.bias], 0)
                               .detach().float().contiguous())
-        qkv = ops.linear(x, wqkv, bqkv)                            # (B, N, 3C): one GEMM
+            bqkv_lp = wcache.get(attn, "bqkv", (attn.to_q.bias, attn.to_k.bias, attn.to_v.bias), lambda: bqkv.to(compute_dtype()))
+        qkv = ops.linear(x, wqkv, bqkv, bias_lp=bqkv_lp)           # (B, N, 3C): one GEMM
         o = ops.self_attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], attn.heads)
         return _finish(attn, o, residual, shape4, out_dtype)

@@ -5,8 +5,12 @@
 // 8f row f4).  The library path writes the (M, 2 inner) projection to HBM and reads it back in a separate GEGLU pass - the
 // largest activation of the network (545 MB at 104 x 1024 x 2560); here it never leaves the SM.
 //
-// Persistent CTA per SM, tile = 128 rows x (128 value + 128 gate) columns:
-//   warp 8   TMA producer: ring of K-blocks {X 128x64, W_v 128x64, W_g 128x64} (128-byte swizzle, zero-filled edges);
+// Persistent CTA per SM, tile = 128 rows x (128 value + 128 gate) columns.  CTAs run as clusters of two that work on the same
+// columns of two adjacent 128-row blocks: each CTA fetches ONE half of the shared weight tile (rank 0: W_v, rank 1: W_g) and
+// TMA-multicasts it into both CTAs' shared memory, which cuts the L2 -> SM operand traffic of the pair from 96 to 64 KB per
+// K-block (the one-CTA version of this tile is bound by exactly that traffic); the MMAs stay per-CTA (cta_group::1).
+//   warp 8   TMA producer: ring of K-blocks {X 128x64, W_v 128x64, W_g 128x64} (128-byte swizzle, zero-filled edges); a
+//            stage is reused once BOTH CTAs' MMAs have read it (their commits are multicast to both `empty` barriers);
 //   warp 9   one elected thread issues tcgen05.mma (SS, M128 x N256 x K16) into one of two 256-column TMEM accumulators;
 //   warps 0-7  epilogue of the other accumulator: warps 0-3 own the 128 rows for columns [0,64), warps 4-7 for [64,128):
 //            tcgen05.ld value + gate, bias, GELU, 16-bit pack, swizzled staging panel, TMA store (rows beyond M clipped).
@@ -46,6 +50,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
@@ -82,15 +105,16 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ 
     Bars<STAGES>* bars = reinterpret_cast<Bars<STAGES>*>(sBias + 512);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = (M + BMR - 1) / BMR, nt = inner / BNH;
-    const int tiles = mt * nt;
-    const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int rank = (int)cluster_rank(), cluster = (int)blockIdx.x >> 1, nclusters = (int)gridDim.x >> 1;
+    const int nt = inner / BNH;
+    const int pairs = ((M + 2 * BMR - 1) / (2 * BMR)) * nt;         // pair = two adjacent row blocks x one column block
+    const int my_tiles = (pairs - cluster + nclusters - 1) / nclusters;
     const int kblocks = (K + BK - 1) / BK;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->empty[s], 2);                            // this CTA's and its peer's MMA commits
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 1);
@@ -104,6 +128,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ 
     }
     fence_before();
     __syncthreads();
+    cluster_sync();                                                   // the peer's barriers exist before anything is multicast
     fence_after();
     const uint32_t tmem = bars->tmem_base;
 
@@ -113,16 +138,15 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ 
             // row block are shared by the CTAs working on its neighbours and stay in L2; W is L2-resident throughout)
             uint32_t it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-                const int m0 = (tile / nt) * BMR, n0 = (tile % nt) * BNH;
+                const int pair = cluster + i * nclusters;
+                const int m0 = (pair / nt) * 2 * BMR + rank * BMR, n0 = (pair % nt) * BNH;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t st = it % STAGES;
                     mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&bars->full[st], STAGE_BYTES);
+                    mbar_expect_tx(&bars->full[st], STAGE_BYTES);          // X + my half of W + the peer's half
                     const uint32_t base = smem_u32(sStage + st * STAGE_BYTES);
                     tma_load_2d(base, &tx, &bars->full[st], kb * BK, m0);
-                    tma_load_2d(base + A_BYTES, &tw, &bars->full[st], kb * BK, n0);
-                    tma_load_2d(base + A_BYTES + B_BYTES / 2, &tw, &bars->full[st], kb * BK, inner + n0);
+                    tma_load_2d_mc(base + A_BYTES + rank * (B_BYTES / 2), &tw, &bars->full[st], kb * BK, rank * inner + n0, (uint16_t)3);
                 }
             }
         }
@@ -144,7 +168,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         mma_ss(tmem + a * 256, desc_add(da, k * 32), desc_add(db, k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-                    mma_commit(&bars->empty[st]);
+                    mma_commit_mc(&bars->empty[st], (uint16_t)3);
                     if (kb + 1 == kblocks) mma_commit(&bars->acc_full[a]);
                 }
                 __syncwarp();
@@ -157,8 +181,8 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ 
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool store_leader = tid == 0;
         for (int i = 0; i < my_tiles; ++i) {
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-            const int m0 = (tile / nt) * BMR, n0 = (tile % nt) * BNH;
+            const int pair = cluster + i * nclusters;
+            const int m0 = (pair / nt) * 2 * BMR + rank * BMR, n0 = (pair % nt) * BNH;
             const int a = i & 1;
             float* bs = sBias + a * 256;
             // the staging panels and bias slots of accumulator a were last used by tile i - 2: its store must have left them
@@ -213,6 +237,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ 
     }
     fence_before();
     __syncthreads();
+    cluster_sync();                                                   // no CTA leaves while its peer may still signal its barriers
     if (warp == 9) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
@@ -239,11 +264,30 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMa
                   cudaStream_t s) {
     constexpr int STAGES = 3;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 4 * OUT_PANEL + 512 * sizeof(float) + sizeof(Bars<STAGES>) + 1024;
-    const int64_t tiles = ((M + BMR - 1) / BMR) * (inner / BNH);
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    const int64_t pairs = ((M + 2 * BMR - 1) / (2 * BMR)) * (inner / BNH);
     auto kern = ff_geglu_kernel<T, STAGES>;
     if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ff_geglu smem")) return 2;
-    kern<<<grid, NTHREADS, smem, s>>>(tx, tw, ty, bias, (int)M, K, inner);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(NTHREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    static int max_clusters = 0;                       // co-resident CTA pairs (one CTA per SM): the persistent grid
+    if (max_clusters == 0) {
+        cfg.gridDim = dim3(num_sms() & ~1, 1, 1);
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = num_sms() / 2;
+    }
+    const int clusters = (int)(pairs < max_clusters ? pairs : max_clusters);
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    const int Mi = (int)M;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, bias, Mi, K, inner);
+    if (e != cudaSuccess) return cuda_ok(e, "dadd_ff_geglu_fwd launch");
     return launched("dadd_ff_geglu_fwd");
 }
 

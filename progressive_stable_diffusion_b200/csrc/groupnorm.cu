@@ -63,17 +63,22 @@ static GnPlan gn_plan(int B, int C, int HW) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict__ x, const float* __restrict__ chan_add,
+__global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ x2, int C1,
+                                                            const float* __restrict__ chan_add,
                                                             int64_t add_stride, float2* __restrict__ part, int HW, int C, int G,
                                                             int npx) {
     extern __shared__ float smem[];      // [PH][C] x 2
     const int V = C >> 3, PH = blockDim.x / V;
     const int tid = threadIdx.x, v = tid % V, ph = tid / V, c0 = v << 3;
     const int b = blockIdx.y, chunk = blockIdx.x, cpg = C / G;
-    const T* xs = x + (size_t)b * HW * C;
+    // two-source form (x2 != nullptr): the input is the channel concatenation [x | x2] with C1 and C - C1 channels
+    const int C2 = C - C1;
+    const T* xs1 = x + (size_t)b * HW * C1;
+    const T* xs2 = x2 ? x2 + (size_t)b * HW * C2 : nullptr;
     const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
     const int p0 = chunk * npx, p1 = min(HW, p0 + npx);
-    const T* xp = xs + c0;
+    const int sC = c0 >= C1 ? C2 : C1;                  // this thread's source and its row stride
+    const T* xp = c0 >= C1 ? xs2 + (c0 - C1) : xs1 + c0;
     int p = p0 + ph;
     // first batch of loads goes out before anything else
     constexpr int U = 4;
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict_
     const bool full0 = p + (U - 1) * PH < p1;
     if (full0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * sC);
     }
     float sh[8];                                        // chan_add[c] - K_g(c),  K_g = x[b][0][g*cpg] + chan_add[g*cpg]
     {
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int cg = g * cpg;
-            const float k = to_f(xs[cg]) + (addb ? addb[cg] : 0.0f);
+            const float k = to_f(cg < C1 ? xs1[cg] : xs2[cg - C1]) + (addb ? addb[cg] : 0.0f);
             sh[i] = (addb ? addb[c0 + i] : 0.0f) - k;
             if (++r == cpg) { r = 0; ++g; }
         }
@@ -110,12 +115,12 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict_
     }
     for (; p + (U - 1) * PH < p1; p += U * PH) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * sC);
 #pragma unroll
         for (int u = 0; u < U; ++u) acc(t[u]);
     }
     for (; p < p1; p += PH) {
-        t[0].load(xp + (size_t)p * C);
+        t[0].load(xp + (size_t)p * sC);
         acc(t[0]);
     }
     float* s1 = smem;
@@ -139,28 +144,34 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const T* __restrict_
     }
 }
 
+// (mean, rstd) of group g of sample b from the chunk partials (shifted sums around K_g)
 template <typename T>
-__global__ void __launch_bounds__(256) gn_final_kernel(const float2* __restrict__ part, const T* __restrict__ x,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+__device__ __forceinline__ float2 gn_group_stats(const float2* __restrict__ part, const T* __restrict__ x, const T* __restrict__ x2, int C1,
+                                                 const float* addb, int b, int g, int chunks, int HW, int C, int G, float eps) {
+    const int cpg = C / G;
+    float t1 = 0.0f, t2 = 0.0f;
+    for (int k = 0; k < chunks; ++k) {
+        const float2 w = part[((size_t)b * chunks + k) * G + g];
+        t1 += w.x;
+        t2 += w.y;
+    }
+    const float inv_n = __fdividef(1.0f, (float)cpg * (float)HW);
+    const float m = t1 * inv_n;
+    const float var = fmaxf(t2 - t1 * m, 0.0f) * inv_n;
+    const int cg = g * cpg;
+    const float first = to_f(cg < C1 ? x[(size_t)b * HW * C1 + cg] : x2[(size_t)b * HW * (C - C1) + cg - C1]);
+    return make_float2(first + (addb ? addb[cg] : 0.0f) + m, rsqrtf(var + eps));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_final_kernel(const float2* __restrict__ part, const T* __restrict__ x, const T* __restrict__ x2,
+                                                       int C1, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ chan_add, int64_t add_stride,
                                                        float* __restrict__ coef, int chunks, int HW, int C, int G, float eps) {
     __shared__ float2 grp[GN_MAX_G];
     const int b = blockIdx.x, tid = threadIdx.x, cpg = C / G;
-    const T* xs = x + (size_t)b * HW * C;
     const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
-    if (tid < G) {
-        float t1 = 0.0f, t2 = 0.0f;
-        for (int k = 0; k < chunks; ++k) {
-            const float2 w = part[((size_t)b * chunks + k) * G + tid];
-            t1 += w.x;
-            t2 += w.y;
-        }
-        const float inv_n = __fdividef(1.0f, (float)cpg * (float)HW);
-        const float m = t1 * inv_n;
-        const float var = fmaxf(t2 - t1 * m, 0.0f) * inv_n;
-        const int cg = tid * cpg;
-        grp[tid] = make_float2(to_f(xs[cg]) + (addb ? addb[cg] : 0.0f) + m, rsqrtf(var + eps));
-    }
+    if (tid < G) grp[tid] = gn_group_stats(part, x, x2, C1, addb, b, tid, chunks, HW, C, G, eps);
     __syncthreads();
     float* sc = coef + (size_t)b * 2 * C;
     for (int c = tid; c < C; c += blockDim.x) {
@@ -200,34 +211,55 @@ __device__ __forceinline__ void gn_emit(Vec8<T>& t, const float (&sa)[8], const 
     t.store(dst);
 }
 
+// coef != nullptr: per-channel scale / shift precomputed by gn_final_kernel (many chunks per sample: the VAE decoder);
+// coef == nullptr: every CTA finalises its sample's group statistics itself from the (few) chunk partials - two launches.
 template <typename T>
-__global__ void __launch_bounds__(512) gn_apply_nhwc_kernel(const T* __restrict__ x, const float* __restrict__ coef,
-                                                            T* __restrict__ y, int HW, int C, int apply_silu, int npx) {
+__global__ void __launch_bounds__(512) gn_apply_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ x2, int C1,
+                                                            const float* __restrict__ coef, const float2* __restrict__ part,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ chan_add, int64_t add_stride,
+                                                            T* __restrict__ y, int HW, int C, int G, float eps, int apply_silu, int npx) {
+    __shared__ float2 grp[GN_MAX_G];
     const int V = C >> 3, PH = blockDim.x / V;
     const int tid = threadIdx.x, v = tid % V, ph = tid / V, c0 = v << 3;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int p0 = chunk * npx, p1 = min(HW, p0 + npx);
-    const T* xp = x + (size_t)b * HW * C + c0;
+    const int C2 = C - C1;
+    const int sC = c0 >= C1 ? C2 : C1;
+    const T* xp = c0 >= C1 ? x2 + (size_t)b * HW * C2 + (c0 - C1) : x + (size_t)b * HW * C1 + c0;
     T* yp = y + (size_t)b * HW * C + c0;
-    const float* sc = coef + (size_t)b * 2 * C + c0;
     int p = p0 + ph;
     constexpr int U = 4;
     Vec8<T> t[U];
     const bool full0 = p + (U - 1) * PH < p1;
     if (full0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * sC);
     }
     float sa[8], sb[8];
-    {
+    if (coef) {
+        const float* sc = coef + (size_t)b * 2 * C + c0;
         const float4 a0 = *reinterpret_cast<const float4*>(sc), a1 = *reinterpret_cast<const float4*>(sc + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(sc + C), b1 = *reinterpret_cast<const float4*>(sc + C + 4);
         sa[0] = a0.x; sa[1] = a0.y; sa[2] = a0.z; sa[3] = a0.w; sa[4] = a1.x; sa[5] = a1.y; sa[6] = a1.z; sa[7] = a1.w;
         sb[0] = b0.x; sb[1] = b0.y; sb[2] = b0.z; sb[3] = b0.w; sb[4] = b1.x; sb[5] = b1.y; sb[6] = b1.z; sb[7] = b1.w;
-        if (apply_silu == 2) {
+    } else {
+        const float* addb = chan_add ? chan_add + (size_t)b * add_stride : nullptr;
+        if (tid < G) grp[tid] = gn_group_stats(part, x, x2, C1, addb, b, tid, gridDim.x, HW, C, G, eps);
+        __syncthreads();
+        const int cpg = C / G;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { sa[i] *= 0.5f; sb[i] *= 0.5f; }
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            const float2 st = grp[c / cpg];
+            const float a = st.y * gamma[c];
+            sa[i] = a;
+            sb[i] = beta[c] + ((addb ? addb[c] : 0.0f) - st.x) * a;
         }
+    }
+    if (apply_silu == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sa[i] *= 0.5f; sb[i] *= 0.5f; }
     }
     if (full0) {
 #pragma unroll
@@ -236,12 +268,12 @@ __global__ void __launch_bounds__(512) gn_apply_nhwc_kernel(const T* __restrict_
     }
     for (; p + (U - 1) * PH < p1; p += U * PH) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * C);
+        for (int u = 0; u < U; ++u) t[u].load(xp + (size_t)(p + u * PH) * sC);
 #pragma unroll
         for (int u = 0; u < U; ++u) gn_emit(t[u], sa, sb, apply_silu, yp + (size_t)(p + u * PH) * C);
     }
     for (; p < p1; p += PH) {
-        t[0].load(xp + (size_t)p * C);
+        t[0].load(xp + (size_t)p * sC);
         gn_emit(t[0], sa, sb, apply_silu, yp + (size_t)p * C);
     }
 }
@@ -641,15 +673,28 @@ static int64_t gn_workspace_bytes(int B, int C, int HW, int G) {
     return (int64_t)B * p.chunks * G * sizeof(float2) + (int64_t)B * 2 * C * sizeof(float);
 }
 
+// The one-launch cluster kernel serves every shape it can hold; the flat passes (stats [-> final] -> apply) take the rest (samples
+// above ~2.3 MB: 512x512 latents, the VAE decoder).  On B200 the two paths are within run-to-run noise of each other for the
+// large-batch 32x32 sites (profiles/r01_groupnorm_paths.txt); DADD_GN_FLAT=1 forces the flat passes, DADD_GN_FLAT_MB=<n> sends
+// activations of at least n MB to them.
+static bool gn_use_flat(const GncPlan& cp, int B, int C, int HW, size_t esize) {
+    static const int force_flat = [] { const char* e = getenv("DADD_GN_FLAT"); return e ? atoi(e) : -1; }();
+    static const long long flat_mb = [] { const char* e = getenv("DADD_GN_FLAT_MB"); return e ? atoll(e) : -1ll; }();
+    if (!cp.ok || force_flat > 0) return true;
+    if (force_flat == 0 || flat_mb < 0) return false;
+    return (long long)B * C * HW * (long long)esize >= (flat_mb << 20);
+}
+
 template <typename T>
-static int launch_nhwc(const T* x, const float* gamma, const float* beta, const float* chan_add, int64_t add_stride, T* y, int B, int C,
-                       int HW, int G, float eps, int silu, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+static int launch_nhwc(const T* x, const T* x2, int C1, const float* gamma, const float* beta, const float* chan_add, int64_t add_stride,
+                       T* y, int B, int C, int HW, int G, float eps, int silu, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
     DADD_REQUIRE(C / 8 <= 512, "dadd_groupnorm_fwd(NHWC)");
-    static const bool force_flat = [] { const char* e = getenv("DADD_GN_FLAT"); return e && atoi(e) != 0; }();
     const GncPlan cp = gnc_plan(B, C, HW, G, sizeof(T));
-    if (cp.ok && !force_flat) return launch_cluster(cp, x, (const T*)nullptr, C, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, s);
+    if (!gn_use_flat(cp, B, C, HW, sizeof(T))) return launch_cluster(cp, x, x2, C1, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, s);
     DADD_REQUIRE(workspace != nullptr && workspace_bytes >= gn_workspace_bytes(B, C, HW, G), "dadd_groupnorm_fwd(NHWC)");
     DADD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dadd_groupnorm_fwd(NHWC)");
+    DADD_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+                 "dadd_groupnorm_fwd(NHWC)");
     const GnPlan p = gn_plan(B, C, HW);
     float* coef = static_cast<float*>(workspace);                                   // [B][2][C], 16-byte aligned rows
     float2* part = reinterpret_cast<float2*>(coef + (size_t)B * 2 * C);             // [B][chunks][G]
@@ -659,11 +704,15 @@ static int launch_nhwc(const T* x, const float* gamma, const float* beta, const 
         if (cuda_ok(cudaFuncSetAttribute(stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "gn smem")) return 2;
     }
     const dim3 grid(p.chunks, B, 1);
-    stats<<<grid, p.threads, smem, s>>>(x, chan_add, add_stride, part, HW, C, G, p.npx);
+    stats<<<grid, p.threads, smem, s>>>(x, x2, C1, chan_add, add_stride, part, HW, C, G, p.npx);
     if (int rc = launched("dadd_groupnorm_fwd(NHWC stats)")) return rc;
-    gn_final_kernel<T><<<B, 256, 0, s>>>(part, x, gamma, beta, chan_add, add_stride, coef, p.chunks, HW, C, G, eps);
-    if (int rc = launched("dadd_groupnorm_fwd(NHWC final)")) return rc;
-    gn_apply_nhwc_kernel<T><<<grid, p.threads, 0, s>>>(x, coef, y, HW, C, silu, p.npx);
+    if (p.chunks > 16) {      // many chunks per sample (the VAE decoder): finalise once per sample instead of once per CTA
+        gn_final_kernel<T><<<B, 256, 0, s>>>(part, x, x2, C1, gamma, beta, chan_add, add_stride, coef, p.chunks, HW, C, G, eps);
+        if (int rc = launched("dadd_groupnorm_fwd(NHWC final)")) return rc;
+    } else {
+        coef = nullptr;
+    }
+    gn_apply_nhwc_kernel<T><<<grid, p.threads, 0, s>>>(x, x2, C1, coef, part, gamma, beta, chan_add, add_stride, y, HW, C, G, eps, silu, p.npx);
     return launched("dadd_groupnorm_fwd(NHWC apply)");
 }
 
@@ -709,40 +758,29 @@ extern "C" int dadd_groupnorm_fwd(const void* x, const float* gamma, const float
     static const bool silu_exact = [] { const char* e = getenv("DADD_SILU_EXACT"); return e && atoi(e) != 0; }();
     if (apply_silu) apply_silu = (dtype != DADD_F32 && layout == DADD_LAYOUT_NHWC && !silu_exact) ? 2 : 1;
     if (layout == DADD_LAYOUT_NHWC)
-        DADD_DISPATCH_ANY(dtype, T, return launch_nhwc((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, workspace, workspace_bytes, s));
+        DADD_DISPATCH_ANY(dtype, T, return launch_nhwc((const T*)x, (const T*)nullptr, C, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, workspace, workspace_bytes, s));
     DADD_DISPATCH_ANY(dtype, T, return launch_nchw((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
     return 1;
 }
 
-static bool gn_cat_plan(int B, int C1, int C2, int HW, int G, int dtype, GncPlan* out) {
-    if (B <= 0 || C1 <= 0 || C2 <= 0 || HW <= 0 || G <= 0 || G > GN_MAX_G) return false;
-    if (C1 % 8 != 0 || C2 % 8 != 0 || (C1 + C2) % G != 0 || !dtype16_ok(dtype)) return false;
-    static const bool force_flat = [] { const char* e = getenv("DADD_GN_FLAT"); return e && atoi(e) != 0; }();
-    const GncPlan cp = gnc_plan(B, C1 + C2, HW, G, 2);
-    if (out) *out = cp;
-    return cp.ok && !force_flat;
-}
-
 extern "C" int dadd_groupnorm_cat_supported(int B, int C1, int C2, int HW, int G, int dtype) {
-    return gn_cat_plan(B, C1, C2, HW, G, dtype, nullptr) ? 1 : 0;
+    return (B > 0 && C1 > 0 && C2 > 0 && HW > 0 && G > 0 && G <= GN_MAX_G && C1 % 8 == 0 && C2 % 8 == 0 && (C1 + C2) % G == 0 &&
+            (C1 + C2) / 8 <= 512 && dtype16_ok(dtype)) ? 1 : 0;
 }
 
 extern "C" int dadd_groupnorm_cat_fwd(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
                                       const float* chan_add, int64_t chan_add_stride, void* y, int B, int HW, int G, float eps,
-                                      int apply_silu, int dtype, void* stream) {
+                                      int apply_silu, int dtype, void* workspace, int64_t workspace_bytes, void* stream) {
     DADD_REQUIRE(x1 && x2 && y && gamma && beta, "dadd_groupnorm_cat_fwd");
     DADD_REQUIRE(B >= 0, "dadd_groupnorm_cat_fwd");
     if (B == 0) return 0;
-    GncPlan cp;
-    if (!gn_cat_plan(B, C1, C2, HW, G, dtype, &cp))
-        return fail("%s: shape not supported by the one-launch cluster kernel (C1 + C2 = %lld, HW = %lld): check "
-                    "dadd_groupnorm_cat_supported() and concatenate on the caller's side", "dadd_groupnorm_cat_fwd",
-                    (long long)C1 + C2, (long long)HW);
+    if (!dadd_groupnorm_cat_supported(B, C1, C2, HW, G, dtype))
+        return fail("%s: needs 16-bit NHWC operands with C1 %% 8 == 0, C2 %% 8 == 0, (C1 + C2) %% G == 0 (C1 + C2 = %lld, HW = %lld)",
+                    "dadd_groupnorm_cat_fwd", (long long)C1 + C2, (long long)HW);
     cudaStream_t s = (cudaStream_t)stream;
     static const bool silu_exact = [] { const char* e = getenv("DADD_SILU_EXACT"); return e && atoi(e) != 0; }();
     if (apply_silu) apply_silu = silu_exact ? 1 : 2;
-    DADD_DISPATCH_16(dtype, T, return launch_cluster(cp, (const T*)x1, (const T*)x2, C1, gamma, beta, chan_add, chan_add_stride, (T*)y, B,
-                                                     C1 + C2, HW, G, eps, apply_silu, s));
+    DADD_DISPATCH_16(dtype, T, return launch_nhwc((const T*)x1, (const T*)x2, C1, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C1 + C2, HW,
+                                                  G, eps, apply_silu, workspace, workspace_bytes, s));
     return 1;
 }
-

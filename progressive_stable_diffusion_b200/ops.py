@@ -129,9 +129,12 @@ def group_norm_cat(x1: torch.Tensor, x2: torch.Tensor, gamma: torch.Tensor, beta
     if chan_add is not None:
         assert chan_add.dtype == torch.float32 and chan_add.shape == (b, c1 + c2) and chan_add.stride(1) == 1
     y = torch.empty((b, c1 + c2, h, w), dtype=x1.dtype, device=x1.device, memory_format=torch.channels_last)
-    _lib.check(_lib.load().dadd_groupnorm_cat_fwd(x1.data_ptr(), c1, x2.data_ptr(), c2, gamma.data_ptr(), beta.data_ptr(),
-                                                  _ptr(chan_add), 0 if chan_add is None else chan_add.stride(0), y.data_ptr(),
-                                                  b, h * w, num_groups, eps, int(silu), _dt(x1), _stream()),
+    lib = _lib.load()
+    ws_bytes = int(lib.dadd_groupnorm_workspace_bytes(b, c1 + c2, h * w, num_groups, NHWC))
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=x1.device)
+    _lib.check(lib.dadd_groupnorm_cat_fwd(x1.data_ptr(), c1, x2.data_ptr(), c2, gamma.data_ptr(), beta.data_ptr(),
+                                          _ptr(chan_add), 0 if chan_add is None else chan_add.stride(0), y.data_ptr(),
+                                          b, h * w, num_groups, eps, int(silu), _dt(x1), ws.data_ptr(), ws_bytes, _stream()),
                "dadd_groupnorm_cat_fwd")
     return y
 
@@ -215,10 +218,12 @@ LINEAR_IMPL = "lib"
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-           out: Optional[torch.Tensor] = None, impl: str = "auto") -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, impl: str = "auto", bias_lp: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.linear(x, w, bias) (+ residual)``: x (..., K) 16-bit, w (N, K) same dtype, bias (N,) fp32, residual (..., N).
     ``impl``: "tc" = the tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``; K % 8 == 0, N a multiple of
-    160 or 256, dense operands), "lib" = library GEMM followed by the fused bias / residual pass, "auto" = ``LINEAR_IMPL``."""
+    160 or 256, dense operands), "lib" = library GEMM followed by the fused bias / residual pass, "auto" = ``LINEAR_IMPL``.
+    ``bias_lp``: the same bias in x's dtype for the library GEMM's own epilogue (callers keep it in ``wcache``; cast on the
+    fly when absent)."""
     _cuda(x, w, bias, residual)
     k, n = x.shape[-1], w.shape[0]
     m = x.numel() // k
@@ -237,28 +242,16 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                                        _stream()), "dadd_linear_fwd")
         return y
     if residual is None:                               # bias in the library GEMM's own epilogue
-        y = torch.nn.functional.linear(x, w, None if bias is None else _bias16(bias, x.dtype))
+        y = torch.nn.functional.linear(x, w, None if bias is None else (bias_lp if bias_lp is not None else bias.to(x.dtype)))
         if out is not None:
             out.copy_(y)
             y = out
         return y
+    if bias is None:                                   # residual only: the library GEMM accumulates onto it (beta = 1)
+        y = torch.empty(shape, dtype=x.dtype, device=x.device) if out is None else out
+        return torch.addmm(residual.reshape(m, n), x.reshape(m, k), w.t(), out=y.view(m, n)).view(shape)
     y = torch.nn.functional.linear(x, w)
     return bias_residual(y, residual, bias, out=y if out is None else out)
-
-
-_BIAS16 = {}
-
-
-def _bias16(bias: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """16-bit copy of an fp32 bias for the library GEMM epilogue (address-stable, rebuilt when the source changes)."""
-    key = (bias.data_ptr(), dtype)
-    hit = _BIAS16.get(key)
-    if hit is None or hit[0] != bias._version or hit[1].numel() != bias.numel():
-        if len(_BIAS16) > 4096:
-            _BIAS16.clear()
-        hit = (bias._version, bias.detach().to(dtype))
-        _BIAS16[key] = hit
-    return hit[1]
 
 
 def ff_geglu(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:

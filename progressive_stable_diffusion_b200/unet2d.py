@@ -56,7 +56,8 @@ def _conv(mod: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
 
 def _linear(mod: nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``mod(x) (+ residual)``: tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``)."""
-    return ops.linear(x, wcache.cast(mod, "w", mod.weight, compute_dtype()), _bias32(mod), residual)
+    return ops.linear(x, wcache.cast(mod, "w", mod.weight, compute_dtype()), _bias32(mod), residual,
+                      bias_lp=None if mod.bias is None else wcache.cast(mod, "b", mod.bias, compute_dtype()))
 
 
 def _conv1x1_weight(mod: nn.Conv2d, cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
@@ -76,13 +77,15 @@ def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor, extra_bias: Optiona
     only these input channels.  ``bias=False`` leaves the bias out (second half of a split GEMM)."""
     w = _conv1x1_weight(mod, cols)
     if not bias:
-        b = None
+        b = b_lp = None
     elif extra_bias is None:
-        b = _bias32(mod)
+        b, b_lp = _bias32(mod), wcache.cast(mod, "b", mod.bias, compute_dtype())
     else:
         b = wcache.get(mod, "b32+", (mod.bias, extra_bias.bias),
                        lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).contiguous())
-    return ops.linear(tokens, w, b, residual, out=out)
+        b_lp = wcache.get(mod, "b+" + str(compute_dtype()), (mod.bias, extra_bias.bias),
+                          lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).to(compute_dtype()).contiguous())
+    return ops.linear(tokens, w, b, residual, out=out, bias_lp=b_lp)
 
 
 def _tokens(x: torch.Tensor) -> torch.Tensor:

@@ -164,14 +164,23 @@ def test_groupnorm_cat_equals_groupnorm_of_concatenation(c1, c2, hw, b, dtype):
     assert (got.float().cpu() - ref).abs().max().item() <= ulp * max(1.0, ref.abs().max().item())
 
 
-def test_groupnorm_cat_rejects_shapes_outside_the_cluster_kernel():
+def test_groupnorm_cat_large_activations_take_the_flat_passes():
+    """A 512x512-latent site (7.9 MB per sample) and a > 48 MB batch: the flat stats/apply kernels read both sources too, and
+    equal the kernel on the materialised concatenation bit for bit."""
     ops = _ops()
-    from progressive_stable_diffusion_b200._lib import DaddError
-    x1 = torch.zeros(1, 640, 64, 64, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
-    x2 = torch.zeros(1, 320, 64, 64, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
-    assert not ops.group_norm_cat_supported(x1, x2, 32)          # 7.9 MB per sample: the flat multi-pass path, caller concatenates
-    with pytest.raises(DaddError):
-        ops.group_norm_cat(x1, x2, torch.ones(960, device=DEV), torch.zeros(960, device=DEV), 32, 1e-5, True)
+    for b, c1, c2, hw in ((2, 640, 320, 64), (60, 320, 320, 32)):
+        g = torch.Generator().manual_seed(b + hw)
+        x1 = torch.randn(b, c1, hw, hw, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+        x2 = (torch.randn(b, c2, hw, hw, generator=g) * 0.5 + 1).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+        gamma, beta = (1 + 0.2 * torch.randn(c1 + c2, generator=g)).to(DEV), (0.2 * torch.randn(c1 + c2, generator=g)).to(DEV)
+        add = torch.randn(b, c1 + c2, generator=g).to(DEV)
+        assert ops.group_norm_cat_supported(x1, x2, 32)
+        cat = torch.cat([x1, x2], dim=1).contiguous(memory_format=torch.channels_last)
+        want = ops.group_norm(cat, gamma, beta, 32, 1e-5, True, add)
+        got = ops.group_norm_cat(x1, x2, gamma, beta, 32, 1e-5, True, add)
+        assert torch.equal(got, want)
+        ref = F.silu(F.group_norm(cat[:2].float().cpu() + add[:2].cpu()[:, :, None, None], 32, gamma.cpu(), beta.cpu(), 1e-5))
+        assert (got[:2].float().cpu() - ref).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("b,c,hw", [(26, 320, 32), (13, 128, 128), (5, 960, 32), (2, 2560, 4), (1, 64, 200)])
@@ -329,7 +338,9 @@ def test_linear_library_path_for_other_widths():
 
 # ------------------------------------------------------------------------------------------------ attention cores
 SELF_SHAPES = [(1024, 40, 2), (256, 80, 2), (64, 160, 3), (16, 160, 2), (100, 40, 1), (4096, 40, 1), (200, 64, 1),
-               (130, 128, 1), (256, 160, 2), (1024, 80, 1), (128, 40, 3), (384, 72, 1)]
+               (130, 128, 1), (256, 160, 2), (1024, 80, 1), (128, 40, 3), (384, 72, 1),
+               # even numbers of 256-row items per head -> the two-CTA cluster form with multicast K/V (ragged: 900, 1000)
+               (512, 40, 3), (512, 80, 2), (900, 40, 2), (1000, 64, 1), (2048, 40, 1)]
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
