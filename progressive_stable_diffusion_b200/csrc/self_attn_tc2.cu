@@ -108,29 +108,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                  : "memory");
 }
 
-// multicast variants for the two-CTA cluster form (MC): a K/V tile is fetched once per CTA PAIR - each CTA loads half of its
-// rows and multicasts them into both CTAs' shared memory - and a stage is released when both CTAs' MMAs have consumed it
-__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                               uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-        ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
 // TRACE (debug builds of the timeline only, DADD_ATTN_TRACE=<file>): CTA 0 records clock64() at the protocol events of its
 // first 64 steps into trace[role][step][event], role 0/1 = softmax group leaders, 2 = MMA issuer.
 #define DADD_TRACE_EVENT(role, step, ev)                                                           \
@@ -140,7 +117,7 @@ __device__ __forceinline__ uint32_t cluster_rank() {
         }                                                                                           \
     } while (0)
 
-template <typename T, int NP, int BN_, int STAGES, bool TRACE, int POLY, bool MC>
+template <typename T, int NP, int BN_, int STAGES, bool TRACE, int POLY>
 __global__ void __launch_bounds__(NTHREADS, 1)
 self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, int B, int H, int N, int d,
@@ -165,13 +142,7 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     const int nkv = (N + BN_ - 1) / BN_;
     const int nq2 = (N + 2 * BM - 1) / (2 * BM);
     const int items = nq2 * H * B;
-    // MC: the two CTAs of a cluster take the items 2u and 2u + 1 (the same (sample, head) since nq2 is even there: one K/V
-    // stream for both), u = cluster + ti * clusters; otherwise item = CTA + ti * CTAs
-    const int rank = MC ? (int)cluster_rank() : 0;
-    const int unit0 = MC ? (int)blockIdx.x >> 1 : (int)blockIdx.x, nunits = MC ? (int)gridDim.x >> 1 : (int)gridDim.x;
-    const int units = MC ? items >> 1 : items;
-    const int my_items = (units - unit0 + nunits - 1) / nunits;
-    auto item_of = [&](int ti) { return MC ? ((unit0 + ti * nunits) << 1) + rank : unit0 + ti * nunits; };
+    const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t steps = (uint32_t)my_items * (uint32_t)nkv;
     const int ksteps = (d + 15) >> 4;
 
@@ -187,7 +158,7 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bars->k_full[s], 1);
             mbar_init(&bars->v_full[s], 1);
-            mbar_init(&bars->kv_empty[s], MC ? 2 : 1);
+            mbar_init(&bars->kv_empty[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -197,7 +168,6 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     }
     fence_before();
     __syncthreads();
-    if constexpr (MC) cluster_sync_all();                           // the peer's barriers exist before anything is multicast
     fence_after();
     const uint32_t tmem = bars->tmem_base;
 
@@ -205,33 +175,23 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer: K/V ring over the step stream
             for (uint32_t it = 0; it < steps; ++it) {
-                const int item = item_of((int)(it / (uint32_t)nkv)), j = (int)(it % (uint32_t)nkv);
+                const int item = (int)blockIdx.x + (int)(it / (uint32_t)nkv) * (int)gridDim.x, j = (int)(it % (uint32_t)nkv);
                 const int h = (item / nq2) % H, b = item / (nq2 * H);
                 const uint32_t st = it % STAGES, use = it / STAGES;
                 mbar_wait(&bars->kv_empty[st], (use & 1) ^ 1);
                 mbar_expect_tx(&bars->k_full[st], NP * KV_PANEL);
+                for (int p = 0; p < NP; ++p)
+                    tma_load_4d(smem_u32(sK + (st * NP + p) * KV_PANEL), &tk, &bars->k_full[st], p * 64, j * BN_, h, b);
                 mbar_expect_tx(&bars->v_full[st], NP * KV_PANEL);
-                if constexpr (MC) {      // my half of the rows of each panel, into both CTAs
-                    constexpr uint32_t HALF = KV_PANEL / 2;
-                    for (int p = 0; p < NP; ++p)
-                        tma_load_4d_mc(smem_u32(sK + (st * NP + p) * KV_PANEL + rank * HALF), &tk, &bars->k_full[st], p * 64,
-                                       j * BN_ + rank * (BN_ / 2), h, b, (uint16_t)3);
-                    for (int p = 0; p < NP; ++p)
-                        tma_load_4d_mc(smem_u32(sV + (st * NP + p) * KV_PANEL + rank * HALF), &tv, &bars->v_full[st], p * 64,
-                                       j * BN_ + rank * (BN_ / 2), h, b, (uint16_t)3);
-                } else {
-                    for (int p = 0; p < NP; ++p)
-                        tma_load_4d(smem_u32(sK + (st * NP + p) * KV_PANEL), &tk, &bars->k_full[st], p * 64, j * BN_, h, b);
-                    for (int p = 0; p < NP; ++p)
-                        tma_load_4d(smem_u32(sV + (st * NP + p) * KV_PANEL), &tv, &bars->v_full[st], p * 64, j * BN_, h, b);
-                }
+                for (int p = 0; p < NP; ++p)
+                    tma_load_4d(smem_u32(sV + (st * NP + p) * KV_PANEL), &tv, &bars->v_full[st], p * 64, j * BN_, h, b);
             }
         }
     } else if (warp == 10) {
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer: the two query tiles of each item
             for (int ti = 0; ti < my_items; ++ti) {
-                const int item = item_of(ti);
+                const int item = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int qb = item % nq2, h = (item / nq2) % H, b = item / (nq2 * H);
                 for (int q = 0; q < 2; ++q) {
                     mbar_wait(&bars->q_empty[q], (ti & 1) ^ 1);             // the previous item's QK^T MMAs are done with this tile
@@ -281,10 +241,7 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
                         mma_ts(tO + p * 64, tP + kk * 8, desc_add(dv, kk * 2048), IDESC_PV, (acc || kk > 0) ? 1u : 0u);
                 }
                 mma_commit(&bars->pv_done[q]);
-                if (q == 1) {
-                    if constexpr (MC) mma_commit_mc(&bars->kv_empty[st], (uint16_t)3);
-                    else mma_commit(&bars->kv_empty[st]);
-                }
+                if (q == 1) mma_commit(&bars->kv_empty[st]);
             }
             __syncwarp();
         };
@@ -334,7 +291,7 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         if (q == 1 && steps > 0) named_arrive(1, 256);             // group 0 takes the first turn on the MUFU pipe
         uint32_t s = 0;
         for (int ti = 0; ti < my_items; ++ti) {
-            const int item = item_of(ti);
+            const int item = (int)blockIdx.x + ti * (int)gridDim.x;
             const int qb = item % nq2, h = (item / nq2) % H, b = item / (nq2 * H);
             float m_used = -INFINITY, l = 0.0f;
             for (int j = 0; j < nkv; ++j, ++s) {
@@ -510,25 +467,24 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     }
     fence_before();
     __syncthreads();
-    if constexpr (MC) cluster_sync_all();                           // no CTA leaves while its peer may still signal its barriers
     if (warp == 9) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
     }
 }
 
-template <typename T, int NP, int BN_, int STAGES, int POLY, bool MC>
+template <typename T, int NP, int BN_, int STAGES, int POLY>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int B, int H, int N,
                   int d, float scale, cudaStream_t s) {
     const size_t smem = (size_t)4 * NP * 128 * 128 + (size_t)2 * STAGES * NP * BN_ * 128 + sizeof(Bars<STAGES>) + 1024;
     const int items = ((N + 2 * BM - 1) / (2 * BM)) * H * B;
     const int grid = items < num_sms() ? items : num_sms();
     const float sl2 = scale * 1.4426950408889634f;
-    if constexpr (std::is_same_v<T, __nv_bfloat16> && NP == 1 && !MC) {
+    if constexpr (std::is_same_v<T, __nv_bfloat16> && NP == 1) {
         // debugging aid: DADD_ATTN_TRACE=<file> dumps CTA 0's event timeline of every launch (synchronises; never in a product run)
         static const char* trace_path = getenv("DADD_ATTN_TRACE");
         if (trace_path) {
-            auto tk_ = self_attn_tc2_kernel<T, NP, BN_, STAGES, true, POLY, false>;
+            auto tk_ = self_attn_tc2_kernel<T, NP, BN_, STAGES, true, POLY>;
             if (cuda_ok(cudaFuncSetAttribute(tk_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "self_attn_tc2 smem")) return 2;
             long long* buf = nullptr;
             const size_t n = 3 * 64 * 16;
@@ -547,32 +503,8 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
             return launched("dadd_self_attn_fwd(tcgen05 v2 trace)");
         }
     }
-    auto kern = self_attn_tc2_kernel<T, NP, BN_, STAGES, false, POLY, MC>;
+    auto kern = self_attn_tc2_kernel<T, NP, BN_, STAGES, false, POLY>;
     if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "self_attn_tc2 smem")) return 2;
-    if constexpr (MC) {
-        cudaLaunchConfig_t cfg{};
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cfg.blockDim = dim3(NTHREADS, 1, 1);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        static int max_clusters = 0;                   // co-resident CTA pairs (one CTA per SM): the persistent grid
-        if (max_clusters == 0) {
-            cfg.gridDim = dim3(num_sms() & ~1, 1, 1);
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = num_sms() / 2;
-        }
-        const int pairs = items / 2;
-        cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters), 1, 1);
-        long long* no_trace = nullptr;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, to, B, H, N, d, sl2, no_trace);
-        if (e != cudaSuccess) return cuda_ok(e, "dadd_self_attn_fwd(tcgen05 v2, cluster) launch");
-        return launched("dadd_self_attn_fwd(tcgen05 v2, cluster)");
-    }
     kern<<<grid, NTHREADS, smem, s>>>(tq, tk, tv, to, B, H, N, d, sl2, nullptr);
     return launched("dadd_self_attn_fwd(tcgen05 v2)");
 }
@@ -585,28 +517,21 @@ int self_attn_tc2(const void* q, const void* k, const void* v, int64_t qs, int64
                   int H, int N, int d, float scale, int dtype, cudaStream_t s) {
     const int np = (d + 63) / 64;
     const int bn = np == 1 ? 128 : 64;
-    // Two-CTA clusters that share one K/V stream (each CTA fetches half of every tile and multicasts it): needs an even
-    // number of 256-row items per (sample, head).  DADD_ATTN_MC=0 forces the single-CTA form.
-    static const int poly = getenv("DADD_ATTN_POLY") ? atoi(getenv("DADD_ATTN_POLY")) : 0;      // tuning aid, see below
-    static const bool mc_env = [] { const char* e = getenv("DADD_ATTN_MC"); return (!e || atoi(e) != 0) && !getenv("DADD_ATTN_TRACE"); }();
-    const bool mc = mc_env && poly != 2 && (((N + 2 * tc::BM - 1) / (2 * tc::BM)) % 2 == 0);
     CUtensorMap tq, tk, tv, to;
-    if (tc::make_map(&tq, q, qs, B, H, N, d, dtype, 128) || tc::make_map(&tk, k, ks, B, H, N, d, dtype, mc ? bn / 2 : bn) ||
-        tc::make_map(&tv, v, vs, B, H, N, d, dtype, mc ? bn / 2 : bn) || tc::make_map(&to, o, os, B, H, N, d, dtype, 128))
+    if (tc::make_map(&tq, q, qs, B, H, N, d, dtype, 128) || tc::make_map(&tk, k, ks, B, H, N, d, dtype, bn) ||
+        tc::make_map(&tv, v, vs, B, H, N, d, dtype, bn) || tc::make_map(&to, o, os, B, H, N, d, dtype, 128))
         return 1;
     // Share of the exponentials computed by the FMA-pipe polynomial, in pairs per 16.  Measured on B200 (N = 1024, d = 40,
     // B = 26): 0 -> 86.4 us, 2 -> 87.8, 3 -> 91.5, 4 -> 99.5 (profiles/r01_attn_poly_exp.txt): on sm_100a FFMA2/FADD2 issue at
     // half rate, so the polynomial costs the FMA pipe as many cycles per element as MUFU.EX2 costs the XU pipe and the
     // softmax warps (one per scheduler and turn) become issue-bound.  Default 0; DADD_ATTN_POLY=2 selects the mixed variant.
-#define DADD_TC2(NPV, BNV, STG, PL, MCV) \
-    DADD_DISPATCH_16(dtype, T, return (tc2::launch<T, NPV, BNV, STG, PL, MCV>(tq, tk, tv, to, B, H, N, d, scale, s)))
+    static const int poly = getenv("DADD_ATTN_POLY") ? atoi(getenv("DADD_ATTN_POLY")) : 0;
+#define DADD_TC2(NPV, BNV, STG, PL) DADD_DISPATCH_16(dtype, T, return (tc2::launch<T, NPV, BNV, STG, PL>(tq, tk, tv, to, B, H, N, d, scale, s)))
     if (np == 1) {
-        if (poly == 2) DADD_TC2(1, 128, 4, 2, false);
-        if (mc) DADD_TC2(1, 128, 4, 0, true);
-        DADD_TC2(1, 128, 4, 0, false);
+        if (poly == 2) DADD_TC2(1, 128, 4, 2);
+        DADD_TC2(1, 128, 4, 0);
     }
-    if (mc) DADD_TC2(2, 64, 3, 0, true);
-    DADD_TC2(2, 64, 3, 0, false);
+    DADD_TC2(2, 64, 3, 0);
 #undef DADD_TC2
     return 1;
 }
