@@ -324,7 +324,11 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        try:
+            run_b200(args)
+        finally:
+            from progressive_stable_diffusion_b200 import parallel
+            parallel.shutdown()
 
 
 if __name__ == "__main__":

@@ -34,8 +34,15 @@ def init_from_env(backend: Optional[str] = None) -> tuple:
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local, world
+
+
+def shutdown() -> None:
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def barrier() -> None:

@@ -179,3 +179,47 @@ def test_eta_sampling_uses_reference_rng_order(models):
     torch.manual_seed(8)
     c = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, eta=0.5, steer_scale=1.0)
     assert not torch.equal(a, c)
+
+
+def test_unet_noise_prediction_512(models, compute):
+    """BASELINE config 5 (512x512 -> 64x64 latents): N = 4096 self-attention, tcgen05 cross-attention at N = 4096 / 1024, the
+    flat GroupNorm passes (samples above the cluster kernel's shared-memory budget) and their two-source form on the up path."""
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import _prepare_conditioning, _set_delta_scale_on_processors
+    module, state, gain, cache = models
+    if gain != 1.0:
+        pytest.skip("one weight set is enough for the large-latent run")
+    uw, aw, pw, _ = _split(state)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 4, 64, 64, generator=g)
+    img = torch.randn(1, 16, 768, generator=g)
+    target, source, t = torch.tensor([2.25]), torch.tensor([0.0]), torch.tensor([700])
+    with torch.no_grad():
+        cond_ref = conditioning.prepare_conditioning(aw, pw, target, source, img)
+        eps_ref = _memo(cache, "eps512", lambda: ounet.unet_forward(uw, x, t, cond_ref, ounet.CrossCfg(True, 3.0)))
+        cond = _prepare_conditioning(module, target.to(DEV), source.to(DEV), img.to(DEV))
+        _set_delta_scale_on_processors(module, 3.0)
+        eps = module(x.to(DEV), t.to(DEV), cond)
+    assert eps.shape == (1, 4, 64, 64)
+    e = rel_err(eps, eps_ref)
+    print(f"eps rel err 512x512 {compute}: {e:.4g}")
+    assert e <= TOL_EPS[compute], e
+
+
+def test_evaluation_sweep_sharded_equals_single_process(models):
+    """BASELINE config 4 in miniature: a sorted job list run as one process and as two ranks' shares gives the same latents
+    job by job (all initial noise is drawn up front in job order), and padding the last batch does not leak."""
+    from progressive_stable_diffusion_b200.evaluation_pipeline import generate_all
+    module, _, gain, _ = models
+    if gain != 1.0:
+        pytest.skip("one weight set is enough")
+    g = torch.Generator().manual_seed(12)
+    tokens = torch.randn(3, 16, 768, generator=g)
+    jobs = sorted((s, float(s % 4), float(tl)) for s in range(3) for tl in (0, 1, 3))[:7]      # 7 jobs, batches of 4: ragged tail
+    kw = dict(batch_size=4, sampling_steps=3, steer_scale=2.0, seed=5, decode=False)
+    whole = generate_all(module, jobs, tokens, DEV, **kw)
+    parts = {}
+    for r in range(2):
+        parts.update(generate_all(module, jobs, tokens, DEV, rank=r, world_size=2, **kw))
+    assert sorted(whole) == sorted(parts) == list(range(len(jobs)))
+    for i in whole:
+        assert torch.equal(whole[i], parts[i]), i
