@@ -28,7 +28,7 @@ extern "C" {
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
 
-/* ABI version of this header (bumped on any signature change; currently 6). */
+/* ABI version of this header (bumped on any signature change; currently 7). */
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -120,6 +120,10 @@ int dadd_bias_residual_fwd(const void* a, const void* res /* nullable */, const 
  * C % 8 == 0. */
 int dadd_upsample_nearest2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 
+/* y = x * sigmoid(1.702 x): the `quick_gelu` activation of the CLIP ViT-L/14 vision tower (transformers
+ * CLIPVisionModelWithProjection, loaded by the reference at src/models/image_encoder.py:34-38).  n % 8 == 0; y may alias x. */
+int dadd_quick_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
+
 /* GEGLU gate of the transformer feed-forward: y[r][j] = x[r][j] * gelu_erf(x[r][inner + j]), x: [rows][2*inner]. */
 int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, void* stream);
 
@@ -183,7 +187,9 @@ int dadd_self_attn_fwd(const void* q, const void* k, const void* v, int64_t q_st
 /* ------------------------------------------------------------------------------------------------
  * Feature Purifier pieces (src/models/feature_purifier.py:81-95), fp32 (runs once per sampling call).
  * (1) multi-head attention core of nn.MultiheadAttention(768, 8): q [B][Lq][D], k,v [B][Lk][D] (already
- *     in-projected), o [B][Lq][D] (before out_proj); Lq, Lk <= 32, D/heads <= 128.
+ *     in-projected), o [B][Lq][D] (before out_proj); Lq <= 256, D/heads <= 128, and one (sample, head) must fit
+ *     shared memory: ((Lq + 2 Lk)(D/heads + 1) + Lq Lk) floats <= 227 KB.  Also the core of the Perceiver resampler
+ *     (ImageProjectionPlus, src/models/image_encoder.py:213-220: 16 queries over the 257 CLIP patch tokens).
  * (2) gating epilogue: y = LayerNorm(img - sigmoid(gate_logits) * disease; gamma, beta, eps), all [rows][D].
  */
 int dadd_purifier_attn_fwd(const float* q, const float* k, const float* v, float* o, int B, int Lq, int Lk, int D,

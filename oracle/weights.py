@@ -234,6 +234,51 @@ def make_module_state(seed: int = 0, gain: float = 1.0, routing: bool = True,
     return sd
 
 
+def make_clip_vision_state(seed: int = 5, hidden: int = 1024, inter: int = 4096, layers: int = 24, heads: int = 16,
+                           image: int = 224, patch: int = 14, proj: int = 768, affine_jitter: float = 0.1) -> State:
+    """Keys of transformers' ``CLIPVisionModelWithProjection.state_dict()`` (the tower the reference loads at
+    image_encoder.py:34-38).  PyTorch-default-style bounds with gain sqrt(3) so 24 residual layers keep the signal alive."""
+    it = _Init(seed, math.sqrt(3.0), affine_jitter)
+    p = "vision_model."
+    it.sd[p + "embeddings.class_embedding"] = torch.randn(hidden, generator=it.g)
+    b = 1.0 / math.sqrt(3 * patch * patch)
+    it.sd[p + "embeddings.patch_embedding.weight"] = it._u((hidden, 3, patch, patch), b * it.gain)
+    it.sd[p + "embeddings.position_embedding.weight"] = 0.5 * torch.randn((image // patch) ** 2 + 1, hidden, generator=it.g)
+    it.norm(p + "pre_layrnorm", hidden)
+    for i in range(layers):
+        q = f"{p}encoder.layers.{i}."
+        for t in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            it.linear(q + "self_attn." + t, hidden, hidden)
+        it.norm(q + "layer_norm1", hidden)
+        it.linear(q + "mlp.fc1", hidden, inter)
+        it.linear(q + "mlp.fc2", inter, hidden)
+        it.norm(q + "layer_norm2", hidden)
+    it.norm(p + "post_layernorm", hidden)
+    it.linear("visual_projection", hidden, proj, bias=False)
+    return it.sd
+
+
+def make_projection_plus_state(seed: int = 6, clip_hidden: int = 1024, dim: int = 768, num_tokens: int = 16, depth: int = 2,
+                               affine_jitter: float = 0.1) -> State:
+    """Keys of the reference's ``ImageProjectionPlus`` (image_encoder.py:143-191)."""
+    it = _Init(seed, math.sqrt(3.0), affine_jitter)
+    it.sd["latents"] = torch.randn(1, num_tokens, dim, generator=it.g) * 0.5
+    if clip_hidden != dim:
+        it.linear("proj_in", clip_hidden, dim)
+    for i in range(depth):
+        q = f"layers.{i}."
+        b = 1.0 / math.sqrt(dim)
+        it.sd[q + "cross_attn.in_proj_weight"] = it._u((3 * dim, dim), b * it.gain)
+        it.sd[q + "cross_attn.in_proj_bias"] = it._u((3 * dim,), b)
+        it.linear(q + "cross_attn.out_proj", dim, dim)
+        it.linear(q + "ff.0", dim, 4 * dim)
+        it.linear(q + "ff.2", 4 * dim, dim)
+        it.norm(q + "norm1", dim)
+        it.norm(q + "norm2", dim)
+    it.norm("norm_out", dim)
+    return it.sd
+
+
 def sub_state(sd: State, prefix: str) -> State:
     n = len(prefix)
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}

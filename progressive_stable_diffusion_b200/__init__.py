@@ -12,6 +12,7 @@ from .attention_processor_routing_gates import (SplitInjectionAttentionProcessor
                                                 set_split_injection_processors)
 from .diffusion_module_ip import DiffusionIPConfig, DiffusionModuleWithIP, default_config, load_config  # noqa: F401
 from .feature_purifier import FeaturePurifier  # noqa: F401
+from .image_encoder import ImageEncoder, ImageProjection, ImageProjectionPlus  # noqa: F401
 from .ordinal_embedder import AdditiveOrdinalEmbedder  # noqa: F401
 from .unet import OrdinalUNet, UNetConfig  # noqa: F401
 from .vae import SDVAE  # noqa: F401
@@ -20,5 +21,5 @@ __all__ = [
     "AttnProcessor2_0", "compute_dtype", "set_compute_dtype", "OrdinalIPAttnProcessor2_0", "SplitInjectionAttentionProcessor", "get_block_type",
     "get_frequency_mode_for_block", "set_ordinal_ip_attention_processors", "set_split_injection_processors",
     "DiffusionIPConfig", "DiffusionModuleWithIP", "default_config", "load_config", "FeaturePurifier",
-    "AdditiveOrdinalEmbedder", "OrdinalUNet", "UNetConfig", "SDVAE",
+    "AdditiveOrdinalEmbedder", "OrdinalUNet", "UNetConfig", "SDVAE", "ImageEncoder", "ImageProjection", "ImageProjectionPlus",
 ]

@@ -30,6 +30,7 @@ SIGNATURES = {
     "dadd_linear_supported": [_L, _I, _I],
     "dadd_linear_fwd": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "dadd_ff_geglu_fwd": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "dadd_quick_gelu_fwd": [_P, _P, _L, _I, _P],
     "dadd_geglu_fwd": [_P, _P, _L, _I, _I, _P],
     "dadd_cross_attn_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _P],
     "dadd_self_attn_fwd": [_P, _P, _P, _L, _L, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _P],

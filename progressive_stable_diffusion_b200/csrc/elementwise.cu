@@ -85,9 +85,38 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
     }
 }
 
+// CLIP's activation: y = x * sigmoid(1.702 x) (transformers `quick_gelu`, the MLP of the ViT-L/14 tower the reference loads at
+// src/models/image_encoder.py:34-38), vectorised, in place allowed.
+template <typename T>
+__global__ void __launch_bounds__(256) quick_gelu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t nvec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        Vec8<T> t;
+        t.load(x + (i << 3));
+        float f[8];
+        t.unpack(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __fdividef(f[k], 1.0f + __expf(-1.702f * f[k]));
+        t.pack(f);
+        t.store(y + (i << 3));
+    }
+}
+
 }  // namespace daddk
 
 using namespace daddk;
+
+extern "C" int dadd_quick_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
+    DADD_REQUIRE(x && y && n >= 0 && n % 8 == 0, "dadd_quick_gelu_fwd");
+    DADD_REQUIRE(dtype_ok(dtype), "dadd_quick_gelu_fwd");
+    if (n == 0) return 0;
+    const int64_t nvec = n >> 3;
+    int64_t grid = (nvec + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    DADD_DISPATCH_ANY(dtype, T, quick_gelu_kernel<T><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, nvec));
+    return launched("dadd_quick_gelu_fwd");
+}
 
 extern "C" int dadd_upsample_nearest2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
     DADD_REQUIRE(x && y && B >= 0 && H > 0 && W > 0, "dadd_upsample_nearest2x_fwd");

@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ x, T* 
     }
 }
 
-// nn.MultiheadAttention core for the purifier: one CTA per (sample, head); everything in shared memory.
+// nn.MultiheadAttention core for the purifier (16 x 16 tokens) and the Perceiver resampler of the conditioning front end
+// (16 queries x 257 patches): one CTA per (sample, head); everything in shared memory, fp32.
 __global__ void __launch_bounds__(256) purifier_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                             const float* __restrict__ v, float* __restrict__ o, int Lq,
                                                             int Lk, int D, int heads) {
@@ -271,11 +272,14 @@ int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, v
 int dadd_purifier_attn_fwd(const float* q, const float* k, const float* v, float* o, int B, int Lq, int Lk, int D,
                            int heads, void* stream) {
     DADD_REQUIRE(q && k && v && o, "dadd_purifier_attn_fwd");
-    DADD_REQUIRE(B >= 0 && Lq > 0 && Lk > 0 && Lq <= 32 && Lk <= 32, "dadd_purifier_attn_fwd");
+    DADD_REQUIRE(B >= 0 && Lq > 0 && Lk > 0 && Lq <= 256, "dadd_purifier_attn_fwd");
     DADD_REQUIRE(heads > 0 && D % heads == 0 && D / heads <= 128, "dadd_purifier_attn_fwd");
     if (B == 0) return 0;
     const int hd = D / heads;
     const size_t smem = ((size_t)(Lq + 2 * Lk) * (hd + 1) + (size_t)Lq * Lk) * sizeof(float);
+    if (smem > 227 * 1024)
+        return fail("%s: (Lq + 2 Lk) (D / heads + 1) + Lq Lk floats must fit 227 KB of shared memory (Lq = %lld, Lk = %lld)",
+                    "dadd_purifier_attn_fwd", (long long)Lq, (long long)Lk);
     if (smem > 48 * 1024) {
         if (cuda_ok(cudaFuncSetAttribute(purifier_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                     "dadd_purifier_attn_fwd"))

@@ -4,8 +4,10 @@
 ``forward`` :383-390), as a plain ``nn.Module`` (no Lightning).  State-dict keys equal a Lightning checkpoint's
 (``unet.unet.*``, ``vae.vae.*``, ``ordinal_embedder.*``, ``feature_purifier.*``), schedule buffers are non-persistent.
 
-Out of this tier: ``training_step`` / optimisers (f1) and the CLIP + resampler front end (f3) - synthetic
-benchmarks and tests feed ``(B, 16, 768)`` image tokens straight into ``_get_image_embeds``.
+The CLIP + resampler front end (``image_encoder.py``) is built on request (``build_image_encoder=True``
+or a checkpoint that carries its weights): it is 304 M frozen parameters that the synthetic benchmark - which feeds
+``(B, 16, 768)`` image tokens straight into ``_get_image_embeds``, as SURVEY.md 8d allows - does not need.
+Out of this tier: ``training_step`` / optimisers (f1).
 """
 
 from __future__ import annotations
@@ -21,6 +23,7 @@ from torch import Tensor
 from .attention_processor_base import set_ordinal_ip_attention_processors
 from .attention_processor_routing_gates import SplitInjectionAttentionProcessor, set_split_injection_processors
 from .feature_purifier import FeaturePurifier
+from .image_encoder import ImageEncoder, ImageProjection, ImageProjectionPlus
 from .ordinal_embedder import AdditiveOrdinalEmbedder
 from .unet import OrdinalUNet, UNetConfig
 from .vae import SDVAE
@@ -104,7 +107,7 @@ def default_config(**model_overrides) -> AttrDict:
 
 
 class DiffusionModuleWithIP(nn.Module):
-    def __init__(self, cfg: Any, build_vae: bool = True) -> None:
+    def __init__(self, cfg: Any, build_vae: bool = True, build_image_encoder: bool = False) -> None:
         super().__init__()
         self.cfg = cfg
         m, d = cfg.model, cfg.diffusion
@@ -128,8 +131,18 @@ class DiffusionModuleWithIP(nn.Module):
             gate_init_disease=tuple(getattr(m, "gate_init_disease", [0.5, 0.5])),
         )
         self.vae = SDVAE(getattr(m, "pretrained_vae_path", None)) if build_vae else None
-        self.image_encoder = None        # CLIP ViT-L/14 + ImageProjectionPlus: off-path front end
+        self.image_encoder = None        # frozen CLIP tower + trainable projection (reference :130-149)
         self.image_projection = None
+        if build_image_encoder:
+            self.image_encoder = ImageEncoder(pretrained_path=self.diff_cfg.image_encoder_path, torch_dtype=torch.float32)
+            if self.diff_cfg.use_image_projection_plus:
+                self.image_projection = ImageProjectionPlus(clip_hidden_dim=self.image_encoder.hidden_size,
+                                                            cross_attention_dim=m.conditioning_dim,
+                                                            num_tokens=self.diff_cfg.num_image_tokens)
+            else:
+                self.image_projection = ImageProjection(clip_embedding_dim=self.image_encoder.projection_dim,
+                                                        cross_attention_dim=m.conditioning_dim,
+                                                        num_tokens=self.diff_cfg.num_image_tokens)
         emb = m.ordinal_embedder
         self.ordinal_embedder = AdditiveOrdinalEmbedder(
             num_classes=emb.num_classes, embedding_dim=m.embedding_dim,
@@ -172,13 +185,18 @@ class DiffusionModuleWithIP(nn.Module):
 
     # ------------------------------------------------------------------ reference :315-332
     def _get_image_embeds(self, structure_images: Tensor) -> Tensor:
-        """(B, num_image_tokens, conditioning_dim) anatomy tokens.  Already-projected tokens pass through; raw
-        CLIP-preprocessed images need the off-path CLIP + resampler front end, which this tier does not build."""
+        """(B, num_image_tokens, conditioning_dim) anatomy tokens from CLIP-preprocessed pixels (B, 3, 224, 224); tokens that
+        are already projected ``(B, num_image_tokens, conditioning_dim)`` pass through (synthetic benchmarks, cached tokens)."""
         if structure_images.dim() == 3 and structure_images.shape[-1] == self.cfg.model.conditioning_dim:
             return structure_images
-        raise NotImplementedError(
-            "CLIP ViT-L/14 + ImageProjectionPlus are outside the B200 hot path (SURVEY.md 8f, row f3): pass the projected "
-            "(B, 16, 768) image tokens instead of (B, 3, 224, 224) pixels")
+        if self.image_encoder is None:
+            raise RuntimeError("this module was built without the CLIP front end: construct it with build_image_encoder=True "
+                               "(or load a checkpoint that carries image_encoder.* weights), or pass projected (B, 16, 768) tokens")
+        if self.diff_cfg.use_image_projection_plus:
+            image_embeds = self.image_encoder.get_hidden_states(structure_images)
+        else:
+            image_embeds = self.image_encoder(structure_images)
+        return self.image_projection(image_embeds)
 
     def forward(self, latents: Tensor, timesteps: Tensor, cond_embed: Tensor, time_terms: Optional[Tensor] = None) -> Tensor:
         return self.unet(latents, timesteps, cond_embed, time_terms=time_terms)
@@ -202,6 +220,7 @@ class DiffusionModuleWithIP(nn.Module):
         ema_callback.py:316-329) into a module built from ``cfg``."""
         ckpt = torch.load(path, map_location=map_location, weights_only=weights_only)
         state = ckpt.get("state_dict", ckpt)
+        kwargs.setdefault("build_image_encoder", any(k.startswith("image_encoder.") for k in state))
         module = cls(cfg if cfg is not None else default_config(), **kwargs)
         module.load_state_dict(state, strict=strict)
         return module

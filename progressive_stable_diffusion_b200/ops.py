@@ -217,6 +217,14 @@ def geglu(x: torch.Tensor) -> torch.Tensor:
 LINEAR_IMPL = "lib"
 
 
+def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
+    """In place ``x * sigmoid(1.702 x)`` (CLIP's activation)."""
+    _cuda(x)
+    assert x.is_contiguous() and x.numel() % 8 == 0
+    _lib.check(_lib.load().dadd_quick_gelu_fwd(x.data_ptr(), x.data_ptr(), x.numel(), _dt(x), _stream()), "dadd_quick_gelu_fwd")
+    return x
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
            out: Optional[torch.Tensor] = None, impl: str = "auto", bias_lp: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.linear(x, w, bias) (+ residual)``: x (..., K) 16-bit, w (N, K) same dtype, bias (N,) fp32, residual (..., N).

@@ -56,3 +56,26 @@ def aoe_inputs():
     labels = torch.cat([torch.linspace(0, 3, 13), torch.tensor([-0.5, 3.7, 2.999, 1.0])])
     src = torch.full_like(labels, 2.0)
     return w, labels, src
+
+
+# ---- conditioning front end (CLIP vision tower + resamplers), SURVEY.md 8f row f3 --------------------------------------
+def clip_inputs(kind: str):
+    """(dims, seeded CLIPVisionModelWithProjection state dict, seeded pixels): ``tiny`` is CPU-sized, ``l14`` is ViT-L/14."""
+    from oracle import image_front_end as fe
+    dims = fe.CLIP_TINY if kind == "tiny" else fe.CLIP_L14
+    w = weights.make_clip_vision_state(seed=5 if kind == "l14" else 7, **dims)
+    g = torch.Generator().manual_seed(31 if kind == "l14" else 32)
+    pixels = torch.randn(2, 3, dims["image"], dims["image"], generator=g)            # CLIP-normalised pixels are ~N(0, 1)
+    return dims, w, pixels
+
+
+def projection_plus_inputs():
+    return weights.make_projection_plus_state(seed=6)
+
+
+def projection_basic_inputs():
+    it = weights._Init(8, 1.0, 0.1)
+    it.linear("projection", 768, 768 * 4)
+    it.norm("norm", 768)
+    g = torch.Generator().manual_seed(33)
+    return it.sd, torch.randn(3, 768, generator=g)

@@ -97,6 +97,30 @@ def main() -> None:
     np.savez_compressed(os.path.join(HERE, "reference_modules.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, v.dtype)
+    # ---- conditioning front end: the REAL transformers CLIP tower + the verbatim reference resamplers -----------
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    from src.models.image_encoder import ImageProjection, ImageProjectionPlus
+    fe = {}
+    for kind in ("tiny", "l14"):
+        d, w, pixels = cases.clip_inputs(kind)
+        clip = CLIPVisionModelWithProjection(CLIPVisionConfig(
+            hidden_size=d["hidden"], intermediate_size=d["inter"], num_hidden_layers=d["layers"], num_attention_heads=d["heads"],
+            image_size=d["image"], patch_size=d["patch"], projection_dim=d["proj"])).eval()
+        missing, unexpected = clip.load_state_dict(w, strict=False)
+        assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+        o = clip(pixel_values=pixels, output_hidden_states=True)
+        fe[f"clip_{kind}_hidden"] = o.hidden_states[-1].numpy()        # what ImageEncoder.get_hidden_states returns (:82-87)
+        fe[f"clip_{kind}_embeds"] = o.image_embeds.numpy()             # what ImageEncoder.forward returns (:63-68)
+    plus = ImageProjectionPlus(clip_hidden_dim=1024, cross_attention_dim=768, num_tokens=16, num_heads=8, depth=2)
+    plus.load_state_dict(cases.projection_plus_inputs())
+    fe["projection_plus"] = plus(torch.from_numpy(fe["clip_l14_hidden"])).numpy()
+    bw, emb_in = cases.projection_basic_inputs()
+    basic = ImageProjection(clip_embedding_dim=768, cross_attention_dim=768, num_tokens=4)
+    basic.load_state_dict(bw)
+    fe["projection_basic"] = basic(emb_in).numpy()
+    np.savez_compressed(os.path.join(HERE, "front_end.npz"), **fe)
+    for k, v in fe.items():
+        print(k, v.shape, v.dtype)
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ def test_header_declares_the_expected_entry_points():
     names = _declared()
     for n in ("dadd_ddim_step", "dadd_ddim_step_table", "dadd_step_begin", "dadd_groupnorm_fwd", "dadd_layernorm_fwd",
               "dadd_geglu_fwd", "dadd_add_layernorm_fwd", "dadd_groupnorm_cat_fwd", "dadd_groupnorm_cat_supported",
-              "dadd_upsample_nearest2x_fwd", "dadd_ff_geglu_fwd", "dadd_linear_fwd", "dadd_linear_supported", "dadd_bias_residual_fwd", "dadd_groupnorm_workspace_bytes",
+              "dadd_upsample_nearest2x_fwd", "dadd_ff_geglu_fwd", "dadd_quick_gelu_fwd", "dadd_linear_fwd", "dadd_linear_supported", "dadd_bias_residual_fwd", "dadd_groupnorm_workspace_bytes",
               "dadd_cross_attn_fwd", "dadd_self_attn_fwd", "dadd_purifier_attn_fwd",
               "dadd_purifier_gate_ln_fwd", "dadd_aoe_interp_fwd", "dadd_image_post_fwd", "dadd_last_error",
               "dadd_abi_version", "dadd_launch_count", "dadd_reset_launch_count"):
@@ -53,7 +53,7 @@ def test_ctypes_table_covers_the_header(lib):
 
 def test_abi_version_and_error_channel(lib):
     l = lib.load()
-    assert l.dadd_abi_version() == 6
+    assert l.dadd_abi_version() == 7
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = l.dadd_groupnorm_fwd(None, None, None, None, 0, None, 1, 320, 64, 32, 1e-5, 1, 1, 1, None, 0, None)
     assert rc != 0 and b"dadd_groupnorm_fwd" in l.dadd_last_error()

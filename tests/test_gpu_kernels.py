@@ -538,6 +538,73 @@ def test_upsample_nearest2x_bit_exact(shape, dtype):
     assert torch.equal(got.cpu(), want)
 
 
+# ------------------------------------------------------------------------------------------------ CLIP + resampler front end
+FE = np.load(os.path.join(os.path.dirname(__file__), "golden", "front_end.npz"))
+
+
+def test_quick_gelu():
+    ops = _ops()
+    x = torch.randn(3, 257, 4096, generator=torch.Generator().manual_seed(2)) * 3
+    for dtype, tol in ((torch.float32, 2e-6), (torch.bfloat16, 2.0 ** -7), (torch.float16, 2.0 ** -10)):
+        xd = x.to(dtype)
+        ref = xd.float() * torch.sigmoid(1.702 * xd.float())
+        got = ops.quick_gelu_(xd.to(DEV).clone())
+        assert (got.float().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+def test_clip_tower_vs_transformers_golden(compute):
+    """ImageEncoder (ViT-L/14, B200 kernels, 16-bit) vs the REAL transformers CLIPVisionModelWithProjection (fp32) on the
+    same seeded weights and pixels: last hidden states (what the resampler consumes) and the projected embedding."""
+    import progressive_stable_diffusion_b200 as P
+    d, w, pixels = cases.clip_inputs("l14")
+    enc = P.ImageEncoder("openai/clip-vit-large-patch14")
+    enc.image_encoder.load_state_dict(w, strict=True)
+    enc.to(DEV)
+    hidden = enc.get_hidden_states(pixels.to(DEV))
+    embeds = enc(pixels.to(DEV))
+    assert hidden.shape == (2, 257, 1024) and embeds.shape == (2, 768)
+    eh, ee = rel_err(hidden, torch.from_numpy(FE["clip_l14_hidden"])), rel_err(embeds, torch.from_numpy(FE["clip_l14_embeds"]))
+    print(f"CLIP ViT-L/14 {compute}: hidden rel err {eh:.4g}, embeds rel err {ee:.4g}")
+    tol = 3e-2 if compute == torch.bfloat16 else 5e-3
+    assert eh <= tol and ee <= tol, (eh, ee)
+
+
+def test_image_projections_vs_reference_golden():
+    import progressive_stable_diffusion_b200 as P
+    plus = P.ImageProjectionPlus(clip_hidden_dim=1024, cross_attention_dim=768, num_tokens=16, num_heads=8, depth=2)
+    plus.load_state_dict(cases.projection_plus_inputs(), strict=True)
+    plus.to(DEV)
+    with torch.no_grad():
+        got = plus(torch.from_numpy(FE["clip_l14_hidden"]).to(DEV))
+    torch.testing.assert_close(got.cpu(), torch.from_numpy(FE["projection_plus"]), atol=2e-3, rtol=1e-3)
+    bw, emb = cases.projection_basic_inputs()
+    basic = P.ImageProjection(clip_embedding_dim=768, cross_attention_dim=768, num_tokens=4)
+    basic.load_state_dict(bw, strict=True)
+    basic.to(DEV)
+    with torch.no_grad():
+        torch.testing.assert_close(basic(emb.to(DEV)).cpu(), torch.from_numpy(FE["projection_basic"]), atol=2e-3, rtol=1e-3)
+
+
+def test_module_front_end_from_pixels(compute):
+    """_get_image_embeds on CLIP-preprocessed pixels (the reference's call, diffusion_module_ip.py:315-332) vs golden tokens."""
+    import progressive_stable_diffusion_b200 as P
+    _, w, pixels = cases.clip_inputs("l14")
+    module = P.DiffusionModuleWithIP(P.default_config(), build_vae=False, build_image_encoder=True)
+    module.image_encoder.image_encoder.load_state_dict(w, strict=True)
+    module.image_projection.load_state_dict(cases.projection_plus_inputs(), strict=True)
+    assert any(k.startswith("image_encoder.image_encoder.vision_model.encoder.layers.23.mlp.fc2") for k in module.state_dict())
+    module.to(DEV).eval()
+    with torch.no_grad():
+        tokens = module._get_image_embeds(pixels.to(DEV))
+        assert torch.equal(module._get_image_embeds(tokens), tokens)          # projected tokens pass through
+    e = rel_err(tokens, torch.from_numpy(FE["projection_plus"]))
+    print(f"front end pixels -> tokens {compute}: rel err {e:.4g}")
+    assert e <= (3e-2 if compute == torch.bfloat16 else 5e-3), e
+    bare = P.DiffusionModuleWithIP(P.default_config(), build_vae=False)
+    with pytest.raises(RuntimeError):
+        bare._get_image_embeds(pixels)
+
+
 def test_image_post():
     ops = _ops()
     x = torch.linspace(-2, 2, 1001)

@@ -90,7 +90,7 @@ def test_schedule_and_labels(module):
 def test_unet_wrapper_errors(module):
     with pytest.raises(ValueError):
         module.unet(torch.zeros(1, 4, 8, 8), torch.zeros(1, dtype=torch.long), torch.zeros(1, 2, 3, 768))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="build_image_encoder"):      # built without the CLIP front end
         module._get_image_embeds(torch.zeros(1, 3, 224, 224))
     with pytest.raises(NotImplementedError):
         bad = P.default_config()
@@ -125,3 +125,18 @@ def test_oracle_role_map_matches_product():
     for n in cases.cross_attention_processor_names():
         assert weights.role_of(n) == P.get_block_type(n)
         assert oproc.frequency_mode_of(n) == P.get_frequency_mode_for_block(n)
+
+
+def test_front_end_state_dict_keys_equal_transformers_and_reference_layout():
+    """ImageEncoder's keys are transformers' CLIPVisionModelWithProjection keys (minus the non-persistent position_ids buffer
+    of older versions), ImageProjectionPlus's are the reference module's (tests/golden/cases.py states load strictly)."""
+    from tests.golden import cases
+    enc = P.ImageEncoder("openai/clip-vit-large-patch14")
+    assert enc.hidden_size == 1024 and enc.projection_dim == 768
+    want = weights.make_clip_vision_state(seed=1, layers=24)
+    assert set(enc.image_encoder.state_dict()) == set(want)
+    assert all(enc.image_encoder.state_dict()[k].shape == v.shape for k, v in want.items())
+    plus = P.ImageProjectionPlus(clip_hidden_dim=1024, cross_attention_dim=768, num_tokens=16)
+    plus.load_state_dict(cases.projection_plus_inputs(), strict=True)
+    with pytest.raises(ValueError):
+        P.ImageEncoder("openai/some-other-tower")

@@ -52,3 +52,24 @@ def test_aoe_matches_reference():
         d = conditioning.aoe_delta(w, labels, labels)
         _close(d, "aoe_delta_same", atol=0, rtol=0)
         assert d.abs().max().item() == 0.0          # invariant I1
+
+
+# ---- conditioning front end: oracle vs the real transformers CLIP tower / the verbatim reference resamplers --------------
+FE = np.load(os.path.join(os.path.dirname(__file__), "golden", "front_end.npz"))
+
+
+def test_clip_oracle_matches_transformers_tiny():
+    from oracle import image_front_end as fe
+    d, w, pixels = cases.clip_inputs("tiny")
+    hidden, embeds = fe.clip_hidden_states(w, pixels, d["heads"], d["patch"])
+    torch.testing.assert_close(hidden, torch.from_numpy(FE["clip_tiny_hidden"]), atol=2e-5, rtol=1e-5)
+    torch.testing.assert_close(embeds, torch.from_numpy(FE["clip_tiny_embeds"]), atol=2e-5, rtol=1e-5)
+
+
+def test_projection_oracles_match_reference():
+    from oracle import image_front_end as fe
+    hidden = torch.from_numpy(FE["clip_l14_hidden"])
+    got = fe.projection_plus(cases.projection_plus_inputs(), hidden)
+    torch.testing.assert_close(got, torch.from_numpy(FE["projection_plus"]), atol=5e-5, rtol=1e-5)
+    bw, emb = cases.projection_basic_inputs()
+    torch.testing.assert_close(fe.projection_basic(bw, emb, 4, 768), torch.from_numpy(FE["projection_basic"]), atol=2e-5, rtol=1e-5)
