@@ -6,7 +6,8 @@
 One "step" = one progression batch per GPU: P patients x 13 levels go through conditioning (AOE + purifier), 50
 CUDA-graph-replayed denoising steps (UNet + fused DDIM) and the VAE decode, producing P*13 images of 256x256.
 Prints ONE JSON line (rank 0).  ``value``: images/s with inputs resident in HBM, timed with CUDA events over exactly K
-steps (max over ranks).  ``e2e``: the same through the public API ``sample_progressions`` with pinned HOST inputs and a
+steps (max over ranks).  ``e2e``: the same through the public API ``sample_progressions`` with pinned HOST inputs - the
+patients' CLIP-preprocessed structure images, encoded by the CLIP ViT-L/14 + resampler front end inside the call - and a
 device->host read of the finished images inside the timed region.  ``--impl reference`` times the reference's CPU path
 (the oracle port: same graph, PyTorch eager fp32 - diffusers is not installable here) on the box's host cores.
 """
@@ -158,11 +159,12 @@ def run_b200(args) -> None:
     patients, batch = args.patients, args.patients * LEVELS
 
     torch.manual_seed(0)                                          # random-init SD-1.x-shaped weights (PyTorch default inits)
-    module = P.DiffusionModuleWithIP(P.default_config())
+    module = P.DiffusionModuleWithIP(P.default_config(), build_image_encoder=True)     # + random-init CLIP ViT-L/14 + resampler
     module.to(dev).eval()
 
     g = torch.Generator().manual_seed(100 + rank)
     host_tokens = torch.randn(patients, 16, 768, generator=g).pin_memory()
+    host_pixels = torch.randn(patients, 3, 224, 224, generator=g).pin_memory()      # CLIP-preprocessed structure images
     host_source = torch.zeros(patients).pin_memory()
     host_noise = torch.randn(patients, 4, 32, 32, generator=g).pin_memory()
     host_images = torch.empty(batch, 3, 256, 256, dtype=torch.float32).pin_memory()
@@ -176,7 +178,7 @@ def run_b200(args) -> None:
         return _latents_to_images(module, lat)
 
     def step_e2e():
-        imgs = sample_progressions(module, host_tokens, host_source, LEVELS, DDIM_STEPS, dev, steer_scale=STEER,
+        imgs = sample_progressions(module, host_pixels, host_source, LEVELS, DDIM_STEPS, dev, steer_scale=STEER,
                                    init_latents=host_noise)
         host_images.copy_(imgs, non_blocking=True)
 
@@ -285,7 +287,9 @@ def run_b200(args) -> None:
                    "patients_per_gpu": patients, "levels": LEVELS, "ddim_steps": DDIM_STEPS, "images_per_step_per_gpu": batch,
                    "parallelism": f"independent (patient x level) units, {world} rank(s), no data-path collective",
                    "l2": "inputs larger than L2: 1.8 GB of bf16 weights stream through the 126 MB L2 on every UNet pass"},
-        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(host_tokens.numel() * 4 + host_source.numel() * 4 + host_noise.numel() * 4),
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(host_pixels.numel() * 4 + host_source.numel() * 4 + host_noise.numel() * 4),
+                "path": "sample_progressions(host pixels (P,3,224,224) -> CLIP ViT-L/14 + resampler once per patient -> purifier/AOE -> "
+                        "50 graph-replayed steps -> VAE decode) -> pinned host images",
                 "d2h_bytes_per_step": int(host_images.numel() * 4), "ms_per_step": seconds_e2e / args.steps * 1e3},
         "gpu_launches": int(launches),
         "dadd_launches_per_denoising_step": int(eng.launches_per_step),

@@ -45,9 +45,11 @@ def _prepare_conditioning(module, target_labels: Tensor, source_labels: Tensor, 
     routing = getattr(module.diff_cfg, "use_routing_gates", True)
     emb = module.ordinal_embedder
     source_aoe = _tokens(emb(source_labels, is_training=False))
-    if structure_image.shape[0] != batch:
-        structure_image = structure_image.expand(batch, *structure_image.shape[1:])
+    # (the reference expands the one structure image to the batch BEFORE the CLIP tower, :282-283, and encodes 13 identical
+    # copies; the tower is per-sample, so encoding once and expanding the tokens gives the same result)
     image_embeds = module._get_image_embeds(structure_image)
+    if image_embeds.shape[0] != batch:
+        image_embeds = image_embeds.expand(batch, *image_embeds.shape[1:])
     if module.feature_purifier is not None:
         image_embeds = module.feature_purifier(image_embeds, source_aoe)
     if image_scale != 1.0:
@@ -245,8 +247,9 @@ def sample_progressions(module, image_tokens: Tensor, source_labels: Tensor, mes
                         decode: bool = True, use_graph: bool = True) -> Tensor:
     """P patient progressions in one batch: what ``main()`` of the reference does for one patient (:596-640: labels
     ``linspace(0, K-1, mes_steps)``, one shared noise tensor per patient, ``_ddim_sample_ip``, ``_latents_to_images``),
-    for ``P = image_tokens.shape[0]`` patients at once.  ``image_tokens`` (P,16,768) / ``source_labels`` (P,) /
-    ``init_latents`` (P,4,h,w) may live on the host (pinned or not): the copies are part of the call.
+    for ``P = image_tokens.shape[0]`` patients at once.  ``image_tokens``: CLIP-preprocessed structure images (P,3,224,224) -
+    encoded ONCE per patient by the module's CLIP + resampler front end - or already projected tokens (P,16,768);
+    ``source_labels`` (P,) / ``init_latents`` (P,4,h,w); all may live on the host (pinned or not): the copies are part of the call.
     Returns images (P*mes_steps, 3, H, W) fp32 in [0,1] on ``device`` (or the final latents when ``decode=False``)."""
     device = torch.device(device if device is not None else image_tokens.device)
     p = image_tokens.shape[0]
@@ -254,7 +257,10 @@ def sample_progressions(module, image_tokens: Tensor, source_labels: Tensor, mes
     do_cfg = (not routing) and (guidance_scale != 1.0)
     k = module.cfg.dataset.num_classes if hasattr(module.cfg.dataset, "num_classes") else 4
     h = module.cfg.dataset.image_size // 8
-    tokens = image_tokens.to(device, non_blocking=True).repeat_interleave(mes_steps, dim=0)
+    tokens = image_tokens.to(device, non_blocking=True)
+    if tokens.dim() == 4:
+        tokens = module._get_image_embeds(tokens)
+    tokens = tokens.repeat_interleave(mes_steps, dim=0)
     source = source_labels.to(device, non_blocking=True).to(torch.float32).repeat_interleave(mes_steps)
     target = _build_labels(mes_steps, 0.0, float(k - 1), device).repeat(p)
     if init_latents is None:

@@ -223,3 +223,21 @@ def test_evaluation_sweep_sharded_equals_single_process(models):
     assert sorted(whole) == sorted(parts) == list(range(len(jobs)))
     for i in whole:
         assert torch.equal(whole[i], parts[i]), i
+
+
+def test_sample_progressions_from_pixels_encodes_each_patient_once():
+    """Public API from CLIP-preprocessed pixels: the front end runs once per patient (the reference encodes 13 identical copies,
+    inference_pipeline_ip.py:282-283) and the result equals the call on the tokens it produces."""
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import sample_progressions
+    torch.manual_seed(3)
+    module = P.DiffusionModuleWithIP(P.default_config(), build_vae=False, build_image_encoder=True).to(DEV).eval()
+    g = torch.Generator().manual_seed(13)
+    pixels = torch.randn(2, 3, 224, 224, generator=g)
+    noise = torch.randn(2, 4, 32, 32, generator=g)
+    src = torch.tensor([0.0, 2.0])
+    with torch.no_grad():
+        tokens = module._get_image_embeds(pixels.to(DEV))
+        a = sample_progressions(module, pixels, src, 3, 2, DEV, init_latents=noise, decode=False)
+        b = sample_progressions(module, tokens, src, 3, 2, DEV, init_latents=noise, decode=False)
+    assert a.shape == (6, 4, 32, 32) and torch.equal(a, b) and torch.isfinite(a).all()
