@@ -157,6 +157,8 @@ def run_b200(args) -> None:
     dev = torch.device("cuda", local)
     pk = peaks()
     patients, batch = args.patients, args.patients * LEVELS
+    cdt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    P.set_compute_dtype(cdt)
 
     torch.manual_seed(0)                                          # random-init SD-1.x-shaped weights (PyTorch default inits)
     module = P.DiffusionModuleWithIP(P.default_config(), build_image_encoder=True)     # + random-init CLIP ViT-L/14 + resampler
@@ -211,7 +213,7 @@ def run_b200(args) -> None:
         # alone, after a pause that lets the power-capped clocks of the long step recover: the burst peaks are its roofline) ----
         time.sleep(3.0)
         c = SELF_ATTN_H * SELF_ATTN_D
-        qkv = torch.randn(batch, SELF_ATTN_N, 3 * c, device=dev, dtype=torch.bfloat16)
+        qkv = torch.randn(batch, SELF_ATTN_N, 3 * c, device=dev, dtype=cdt)
         reps = 20
         for _ in range(3):
             ops.self_attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], SELF_ATTN_H)
@@ -227,7 +229,7 @@ def run_b200(args) -> None:
         # ---- GroupNorm+SiLU 320ch @32x32 (the most frequent memory-bound kernel); a rotation of input/output pairs larger
         # than the 126 MB L2 so that no launch finds its operands cached ----
         nbuf = max(2, -(-(160 << 20) // (batch * 320 * 32 * 32 * 2 * 2)))
-        xgs = [torch.randn(batch, 320, 32, 32, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        xgs = [torch.randn(batch, 320, 32, 32, device=dev, dtype=cdt).contiguous(memory_format=torch.channels_last)
                for _ in range(nbuf)]
         ygs = [torch.empty_like(x) for x in xgs]
         gam, bet = torch.ones(320, device=dev), torch.zeros(320, device=dev)
@@ -242,9 +244,9 @@ def run_b200(args) -> None:
         gn_s = e0.elapsed_time(e1) / 1e3 / reps
         gn_bytes = xgs[0].numel() * 2 * 2
         # ---- triple-pathway cross-attention N=1024, d=40 (tcgen05 kernel; HBM-bound: Q in + O out) ----
-        qx = [torch.randn(batch, SELF_ATTN_N, c, device=dev, dtype=torch.bfloat16) for _ in range(3)]
-        kc = torch.randn(batch, SELF_ATTN_H, 48, SELF_ATTN_D, device=dev, dtype=torch.bfloat16)
-        vc = torch.randn(batch, SELF_ATTN_H, 48, SELF_ATTN_D, device=dev, dtype=torch.bfloat16)
+        qx = [torch.randn(batch, SELF_ATTN_N, c, device=dev, dtype=cdt) for _ in range(3)]
+        kc = torch.randn(batch, SELF_ATTN_H, 48, SELF_ATTN_D, device=dev, dtype=cdt)
+        vc = torch.randn(batch, SELF_ATTN_H, 48, SELF_ATTN_D, device=dev, dtype=cdt)
         gts = torch.tensor([0.9, 0.1, STEER], device=dev)
         for i in range(3):
             ops.cross_attention(qx[i], kc, vc, gts, SELF_ATTN_H, 16, 3)
@@ -281,7 +283,7 @@ def run_b200(args) -> None:
     print(json.dumps({
         "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": seconds / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": "13 MES levels x 50 DDIM steps, lambda=3, 256x256, SD-1.x-shaped random-init weights, "
                                "CFG off (routing gates), eta=0, VAE decode included",
                    "patients_per_gpu": patients, "levels": LEVELS, "ddim_steps": DDIM_STEPS, "images_per_step_per_gpu": batch,
@@ -322,6 +324,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--patients", type=int, default=8, help="patient progressions per GPU per step (13 images each)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit operand type of the kernels (bf16 = the configuration BASELINE.json names; fp16 = same rate, 3 more mantissa bits)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the timed region run ONE eager denoising step inside cudaProfilerStart/Stop (for the ncu launch list)")
     args = ap.parse_args()
