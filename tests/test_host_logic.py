@@ -140,3 +140,23 @@ def test_front_end_state_dict_keys_equal_transformers_and_reference_layout():
     plus.load_state_dict(cases.projection_plus_inputs(), strict=True)
     with pytest.raises(ValueError):
         P.ImageEncoder("openai/some-other-tower")
+
+
+def test_load_from_checkpoint_reads_the_ema_layout(tmp_path, module):
+    """A Lightning checkpoint written under the reference's EMA callback (src/callbacks/ema_callback.py:316-329) holds the
+    AVERAGED weights in ``state_dict`` and the raw ones in ``current_model_state``: the loader must take the former, the way
+    inference_pipeline_ip.py:587-592 does (strict=False), and leave absent keys at their initial values."""
+    key_u = "unet.unet.mid_block.attentions.0.transformer_blocks.0.attn2.processor.to_k_dis.weight"
+    key_p = "feature_purifier.norm_out.weight"
+    ref = module.state_dict()
+    ema = {key_u: torch.full_like(ref[key_u], 0.25), key_p: torch.full_like(ref[key_p], 1.5)}
+    raw = {key_u: torch.zeros_like(ref[key_u]), key_p: torch.zeros_like(ref[key_p])}
+    path = tmp_path / "last.ckpt"
+    torch.save({"state_dict": ema, "current_model_state": raw, "averaging_state": {"n_averaged": torch.tensor(7)},
+                "epoch": 3, "global_step": 1234}, path)
+    loaded = P.DiffusionModuleWithIP.load_from_checkpoint(str(path), cfg=P.default_config(), weights_only=False, strict=False,
+                                                         build_vae=False)
+    sd = loaded.state_dict()
+    assert torch.equal(sd[key_u], ema[key_u]) and torch.equal(sd[key_p], ema[key_p])
+    assert loaded.image_encoder is None            # no image_encoder.* keys in this checkpoint -> front end not built
+    assert set(sd) == set(module.state_dict())
