@@ -14,6 +14,8 @@ What is different underneath:
 
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -94,6 +96,15 @@ def ddim_schedule(alphas_cumprod: Tensor, T: int, sampling_steps: int, eta: floa
     return ts, table
 
 
+# cuDNN picks each convolution's algorithm by timing the candidates once per shape (the off-path convolutions are 38 % of a
+# step); the flag is scoped to this package's calls.  DADD_CUDNN_BENCHMARK=0 restores cuDNN's heuristics.
+CUDNN_BENCHMARK = os.environ.get("DADD_CUDNN_BENCHMARK", "1") != "0"
+
+
+def _cudnn_flags():
+    return torch.backends.cudnn.flags(enabled=True, benchmark=CUDNN_BENCHMARK)
+
+
 class ProgressionEngine:
     """Static buffers + one captured step graph for a fixed (batch, latent size, steps, eta, cfg, pathways) signature."""
 
@@ -125,8 +136,9 @@ class ProgressionEngine:
     def _step(self) -> None:
         ops.step_begin_(self.state, self.terms_table, self.terms_row)
         m = self.module
-        eps_c = m(self.x, None, self.ehs, time_terms=self.terms_row)
-        eps_u = m(self.x, None, self.ehs_u, time_terms=self.terms_row) if self.do_cfg else None
+        with _cudnn_flags():
+            eps_c = m(self.x, None, self.ehs, time_terms=self.terms_row)
+            eps_u = m(self.x, None, self.ehs_u, time_terms=self.terms_row) if self.do_cfg else None
         ops.ddim_step_table_(self.x, eps_c, eps_u, self.guidance, self.coef, self.state, self.noise, 4.0)
 
     def _refresh_kv(self) -> None:
@@ -274,6 +286,7 @@ def sample_progressions(module, image_tokens: Tensor, source_labels: Tensor, mes
 @torch.no_grad()
 def _latents_to_images(module, latents: Tensor) -> Tensor:
     """vae.decode(latents / latent_scale) -> clamp(-1,1) -> [0,1] (reference :473-486); fp32 (B,3,H,W) on the device."""
-    decoded = module.vae.decode(latents / module.diff_cfg.latent_scale)
+    with _cudnn_flags():
+        decoded = module.vae.decode(latents / module.diff_cfg.latent_scale)
     images = decoded.sample if hasattr(decoded, "sample") else decoded
     return ops.image_post(images).contiguous()
