@@ -140,7 +140,7 @@ def run_reference(args) -> None:
                    "patients_per_gpu": 1, "levels": LEVELS, "ddim_steps": DDIM_STEPS},
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------- B200 arm
@@ -273,8 +273,14 @@ def run_b200(args) -> None:
     value = images_total / seconds
     e2e_value = images_total / seconds_e2e
     launches = eager_launches + args.steps * DDIM_STEPS * eng.launches_per_step
+    # every rank leaves the process group BEFORE rank 0 times the CPU baseline: a rank parked in a collective keeps a host
+    # thread spinning, and one extra busy thread on a fully subscribed OpenMP team slows the baseline ~10x (measured)
+    parallel.barrier()
+    parallel.shutdown()
     if rank != 0:
         return
+    if hasattr(os, "sched_setaffinity"):          # undo any affinity narrowing inherited from the communication library
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
     unet_step, decode, cores = cpu_reference_sample(LEVELS)
     unet_step()
     t_unet, t_dec = unet_step(), decode()
@@ -314,7 +320,7 @@ def run_b200(args) -> None:
         "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
                                    f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},
-    }))
+    }), flush=True)
 
 
 def main() -> None:
@@ -329,14 +335,16 @@ def main() -> None:
     ap.add_argument("--profile-step", action="store_true",
                     help="after the timed region run ONE eager denoising step inside cudaProfilerStart/Stop (for the ncu launch list)")
     args = ap.parse_args()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also times the CPU baseline and needs the host's cores (set before
+    # torch is imported).
+    if int(os.environ.get("RANK", "0")) == 0:
+        os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its banner goes to stdout, which carries the one JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference(args)
     else:
-        try:
-            run_b200(args)
-        finally:
-            from progressive_stable_diffusion_b200 import parallel
-            parallel.shutdown()
+        run_b200(args)
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ extern "C" {
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
 
-/* ABI version of this header (bumped on any signature change; currently 7). */
+/* ABI version of this header (bumped on any signature change; currently 8). */
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -101,10 +101,13 @@ int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
                        int dtype, void* stream);
 
 /* Residual add fused with the LayerNorm that consumes it (BasicTransformerBlock: hidden = attn(...) + hidden;
- * norm_hidden = norm(hidden)):  s = x + r rounded to `dtype` (stored to sum_out when non-NULL),
- * y = LayerNorm(s) * gamma + beta.  Same shapes / limits as dadd_layernorm_fwd; x, r, sum_out, y: [rows][C]. */
-int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out /* nullable */, const float* gamma, const float* beta,
-                           void* y, int64_t rows, int C, float eps, int dtype, void* stream);
+ * norm_hidden = norm(hidden)):  s = x + r rounded to `dtype`, y = LayerNorm(s) * gamma + beta; when sum_out is
+ * non-NULL it receives s, or s + sum_bias[c] when sum_bias (fp32 [C]) is given - the bias of the NEXT residual branch's output
+ * projection (ff.net[2].bias) rides on the stored residual, so that `ff(norm) + hidden` becomes one GEMM that accumulates onto
+ * it.  LayerNorm always sees the unbiased s.  Same shapes / limits as dadd_layernorm_fwd; x, r, sum_out, y: [rows][C]. */
+int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out /* nullable */, const float* sum_bias /* nullable */,
+                           const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps, int dtype,
+                           void* stream);
 
 /* Channel bias and/or residual add in one vectorised pass: y[r][c] = a[r][c] (+ res[r][c]) (+ bias[c]).
  * Replaces the bias add after a library convolution and the residual adds of ResnetBlock2D / Transformer2DModel /

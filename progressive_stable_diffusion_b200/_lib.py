@@ -24,7 +24,7 @@ SIGNATURES = {
     "dadd_groupnorm_cat_supported": [_I, _I, _I, _I, _I, _I],
     "dadd_groupnorm_cat_fwd": [_P, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P],
     "dadd_layernorm_fwd": [_P, _P, _P, _P, _L, _I, _F, _I, _P],
-    "dadd_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
+    "dadd_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "dadd_bias_residual_fwd": [_P, _P, _P, _P, _L, _I, _I, _P],
     "dadd_upsample_nearest2x_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dadd_linear_supported": [_L, _I, _I],

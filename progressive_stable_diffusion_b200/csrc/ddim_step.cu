@@ -104,7 +104,7 @@ using namespace daddk;
 
 extern "C" {
 
-int dadd_abi_version(void) { return 7; }
+int dadd_abi_version(void) { return 8; }
 const char* dadd_last_error(void) { return g_last_error; }
 int64_t dadd_launch_count(void) { return g_launches.load(); }
 void dadd_reset_launch_count(void) { g_launches.store(0); }

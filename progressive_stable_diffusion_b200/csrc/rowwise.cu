@@ -9,11 +9,12 @@ namespace daddk {
 constexpr int LN_MAX_VEC = 8;  // 8 vectors x 8 elements x 32 lanes = C <= 2048
 
 // (optional residual add +) LayerNorm, one warp per row, R rows per warp in flight, the rows packed in registers.
-//   s = x (+ y) rounded to T (written to sum_out when given);  out = LayerNorm(s) * gamma + beta.
+//   s = x (+ y) rounded to T (written to sum_out when given, plus sum_bias[c] when given);  out = LayerNorm(s) * gamma + beta.
 // Exact two-pass mean / variance in fp32.  NV = ceil(C / 256) 16-byte vectors per lane.  All loads of the R rows are
 // issued before the first reduction: R * C * sizeof(T) bytes in flight per warp (the kernel is latency-bound otherwise).
 template <typename T, int NV, int R, bool ADD>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const T* __restrict__ yadd, T* __restrict__ sum_out,
+                                                        const float* __restrict__ sum_bias,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         T* __restrict__ out, int64_t rows, int C, float eps) {
     const int lane = threadIdx.x & 31;
@@ -52,7 +53,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                     for (int i = 0; i < 8; ++i) f[j][i] += g[i];
                     Vec8<T> t;
                     t.pack(f[j]);
-                    if (sum_out) t.store(sum_out + (row0 + r) * C + (iv << 3));
+                    if (sum_out) {
+                        if (sum_bias) {                   // the stored sum (a later residual) carries an extra channel bias
+                            const float4 c0 = *reinterpret_cast<const float4*>(sum_bias + (iv << 3));
+                            const float4 c1 = *reinterpret_cast<const float4*>(sum_bias + (iv << 3) + 4);
+                            const float cb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                            float fb[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) fb[i] = f[j][i] + cb[i];
+                            Vec8<T> tb;
+                            tb.pack(fb);
+                            tb.store(sum_out + (row0 + r) * C + (iv << 3));
+                        } else {
+                            t.store(sum_out + (row0 + r) * C + (iv << 3));
+                        }
+                    }
                     t.unpack(f[j]);                       // LayerNorm sees the rounded sum, like the unfused graph
                 }
 #pragma unroll
@@ -96,15 +111,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
 }
 
 template <typename T, bool ADD>
-static int launch_layernorm(const T* x, const T* yadd, T* sum_out, const float* gamma, const float* beta, T* out, int64_t rows,
-                            int C, float eps, cudaStream_t s) {
+static int launch_layernorm(const T* x, const T* yadd, T* sum_out, const float* sum_bias, const float* gamma, const float* beta, T* out,
+                            int64_t rows, int C, float eps, cudaStream_t s) {
     const int nv = (C / 8 + 31) / 32;
     const int wpb = 8;
 #define DADD_LN(NVV, RR)                                                                                                  \
     do {                                                                                                                  \
         const int64_t per_block = (int64_t)wpb * RR;                                                                      \
         layernorm_kernel<T, NVV, RR, ADD><<<(unsigned)((rows + per_block - 1) / per_block), wpb * 32, 0, s>>>(            \
-            x, yadd, sum_out, gamma, beta, out, rows, C, eps);                                                            \
+            x, yadd, sum_out, sum_bias, gamma, beta, out, rows, C, eps);                                                            \
         return launched("dadd_layernorm_fwd");                                                                            \
     } while (0)
     if constexpr (sizeof(T) == 2) {
@@ -241,18 +256,19 @@ int dadd_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
     DADD_REQUIRE(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 256, "dadd_layernorm_fwd");
     DADD_REQUIRE(dtype_ok(dtype), "dadd_layernorm_fwd");
     if (rows == 0) return 0;
-    DADD_DISPATCH_ANY(dtype, T, return (launch_layernorm<T, false>((const T*)x, nullptr, nullptr, gamma, beta, (T*)y, rows, C, eps,
+    DADD_DISPATCH_ANY(dtype, T, return (launch_layernorm<T, false>((const T*)x, nullptr, nullptr, nullptr, gamma, beta, (T*)y, rows, C, eps,
                                                                    (cudaStream_t)stream)));
     return 1;
 }
 
-int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out, const float* gamma, const float* beta, void* y,
-                           int64_t rows, int C, float eps, int dtype, void* stream) {
+int dadd_add_layernorm_fwd(const void* x, const void* r, void* sum_out, const float* sum_bias, const float* gamma, const float* beta,
+                           void* y, int64_t rows, int C, float eps, int dtype, void* stream) {
     DADD_REQUIRE(x && r && y && gamma && beta && rows >= 0, "dadd_add_layernorm_fwd");
+    DADD_REQUIRE(sum_bias == nullptr || sum_out != nullptr, "dadd_add_layernorm_fwd");
     DADD_REQUIRE(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 256, "dadd_add_layernorm_fwd");
     DADD_REQUIRE(dtype_ok(dtype), "dadd_add_layernorm_fwd");
     if (rows == 0) return 0;
-    DADD_DISPATCH_ANY(dtype, T, return (launch_layernorm<T, true>((const T*)x, (const T*)r, (T*)sum_out, gamma, beta, (T*)y, rows, C,
+    DADD_DISPATCH_ANY(dtype, T, return (launch_layernorm<T, true>((const T*)x, (const T*)r, (T*)sum_out, sum_bias, gamma, beta, (T*)y, rows, C,
                                                                   eps, (cudaStream_t)stream)));
     return 1;
 }

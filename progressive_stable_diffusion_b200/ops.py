@@ -161,16 +161,19 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
 
 
 def add_layer_norm(x: torch.Tensor, r: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-                   want_sum: bool = True):
-    """``s = x + r`` (rounded to the tensor dtype) and ``LayerNorm(s)`` in one pass; returns ``(s or None, norm)``."""
-    _cuda(x, r, gamma, beta)
+                   want_sum: bool = True, sum_bias: Optional[torch.Tensor] = None):
+    """``s = x + r`` (rounded to the tensor dtype) and ``LayerNorm(s)`` in one pass; returns ``(s or None, norm)``.
+    ``sum_bias`` (C,) fp32 is added to the RETURNED sum only (LayerNorm sees ``x + r``): the bias of the output projection of
+    the next residual branch, so that branch's ``proj(...) + s`` is one accumulating GEMM."""
+    _cuda(x, r, gamma, beta, sum_bias)
     assert x.is_contiguous() and r.is_contiguous() and x.shape == r.shape and x.dtype == r.dtype
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
     c = x.shape[-1]
+    assert sum_bias is None or (want_sum and sum_bias.dtype == torch.float32 and sum_bias.numel() == c and sum_bias.is_contiguous())
     s = torch.empty_like(x) if want_sum else None
     y = torch.empty_like(x)
-    _lib.check(_lib.load().dadd_add_layernorm_fwd(x.data_ptr(), r.data_ptr(), _ptr(s), gamma.data_ptr(), beta.data_ptr(),
-                                                  y.data_ptr(), x.numel() // c, c, eps, _dt(x), _stream()),
+    _lib.check(_lib.load().dadd_add_layernorm_fwd(x.data_ptr(), r.data_ptr(), _ptr(s), _ptr(sum_bias), gamma.data_ptr(),
+                                                  beta.data_ptr(), y.data_ptr(), x.numel() // c, c, eps, _dt(x), _stream()),
                "dadd_add_layernorm_fwd")
     return s, y
 

@@ -34,9 +34,9 @@ def init_from_env(backend: Optional[str] = None) -> tuple:
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
-        else:
-            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # (no device_id=: eager NCCL initialisation pins the calling thread's CPU affinity while it runs, and host worker
+        # threads created afterwards inherit the narrowed mask - measured 10x slower CPU baseline on rank 0)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local, world
 
 

@@ -54,10 +54,12 @@ def _conv(mod: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     return y + wcache.cast(mod, "b", mod.bias, compute_dtype()).view(1, -1, 1, 1)
 
 
-def _linear(mod: nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``mod(x) (+ residual)``: tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``)."""
+def _linear(mod: nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = None, bias: bool = True) -> torch.Tensor:
+    """``mod(x) (+ residual)`` through ``ops.linear``; ``bias=False`` leaves the bias out (it already rides on ``residual``)."""
+    if not bias or mod.bias is None:
+        return ops.linear(x, wcache.cast(mod, "w", mod.weight, compute_dtype()), None, residual)
     return ops.linear(x, wcache.cast(mod, "w", mod.weight, compute_dtype()), _bias32(mod), residual,
-                      bias_lp=None if mod.bias is None else wcache.cast(mod, "b", mod.bias, compute_dtype()))
+                      bias_lp=wcache.cast(mod, "b", mod.bias, compute_dtype()))
 
 
 def _conv1x1_weight(mod: nn.Conv2d, cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
@@ -110,10 +112,10 @@ def _ln(mod: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
                           mod.eps)
 
 
-def _add_ln(mod: nn.LayerNorm, x: torch.Tensor, r: torch.Tensor):
-    """(x + r, LayerNorm(x + r)) in one kernel."""
+def _add_ln(mod: nn.LayerNorm, x: torch.Tensor, r: torch.Tensor, sum_bias: Optional[torch.Tensor] = None):
+    """(x + r (+ sum_bias), LayerNorm(x + r)) in one kernel."""
     return ops.add_layer_norm(x, r, wcache.cast(mod, "w", mod.weight, torch.float32),
-                              wcache.cast(mod, "b", mod.bias, torch.float32), mod.eps)
+                              wcache.cast(mod, "b", mod.bias, torch.float32), mod.eps, sum_bias=sum_bias)
 
 
 # ----------------------------------------------------------------------------------------------- modules
@@ -168,8 +170,9 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
-    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        # ``net(x) (+ residual)``: the residual add of the transformer block rides on the output GEMM's epilogue
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, out_bias: bool = True) -> torch.Tensor:
+        # ``net(x) (+ residual)``: the residual add of the transformer block rides on the output GEMM (``out_bias=False``: the
+        # caller has already put net[2].bias on the residual, so the GEMM just accumulates onto it)
         # (slicing the batch so that proj -> GEGLU -> out stays inside L2 was measured slower than one pass: the smaller
         # GEMMs lose more than the L2-resident intermediate gains; profiles/r01_ff_slice_ab.txt)
         proj = self.net[0].proj
@@ -177,7 +180,7 @@ class FeedForward(nn.Module):
             g = ops.ff_geglu(x, wcache.cast(proj, "w", proj.weight, compute_dtype()), _bias32(proj))
         else:
             g = ops.geglu(_linear(proj, x))
-        return _linear(self.net[2], g, residual)
+        return _linear(self.net[2], g, residual, bias=out_bias)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -192,10 +195,11 @@ class BasicTransformerBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
         # hidden = attn(norm(hidden)) + hidden, three times; each residual add is fused with the
-        # LayerNorm that follows it, the last one with the feed-forward's output GEMM
+        # LayerNorm that follows it, the last one with the feed-forward's output GEMM: the stored residual already carries
+        # ff.net[2].bias, so ``ff(n) + hidden`` is one GEMM accumulating onto it
         x, n = _add_ln(self.norm2, x, self.attn1(_ln(self.norm1, x)))
-        x, n = _add_ln(self.norm3, x, self.attn2(n, encoder_hidden_states=ehs))
-        return self.ff(n, residual=x)
+        x, n = _add_ln(self.norm3, x, self.attn2(n, encoder_hidden_states=ehs), sum_bias=_bias32(self.ff.net[2]))
+        return self.ff(n, residual=x, out_bias=False)
 
 
 class Transformer2DModel(nn.Module):
