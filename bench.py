@@ -31,6 +31,27 @@ UNET_GFLOP_PER_SAMPLE_STEP = 178.7
 SELF_ATTN_N, SELF_ATTN_D, SELF_ATTN_H = 1024, 40, 8
 
 
+_RESULT_FD = None      # the process's original stdout: carries exactly one JSON line
+
+
+def _claim_stdout() -> None:
+    """Point fd 1 at stderr for the rest of the run (library banners such as NCCL's version line are written straight to fd 1)
+    and keep the original stdout for the result line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(result: dict) -> None:
+    line = (json.dumps(result) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -132,7 +153,7 @@ def run_reference(args) -> None:
     value = LEVELS / progression_s
     sample = (f"{args.steps} timed UNet denoising step(s) at B=13 (oracle port, fp32 eager, {cores} threads) + 1 VAE decode at "
               f"B=13; one 13x50 progression extrapolated as 50 x step + decode = {progression_s:.1f} s")
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": progression_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -140,7 +161,7 @@ def run_reference(args) -> None:
                    "patients_per_gpu": 1, "levels": LEVELS, "ddim_steps": DDIM_STEPS},
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 # --------------------------------------------------------------------------------------------------- B200 arm
@@ -286,7 +307,7 @@ def run_b200(args) -> None:
     t_unet, t_dec = unet_step(), decode()
     cpu_progression = DDIM_STEPS * t_unet + t_dec
     tflops = batch * world * args.steps * DDIM_STEPS * UNET_GFLOP_PER_SAMPLE_STEP / 1e3 / seconds
-    print(json.dumps({
+    _emit({
         "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": seconds / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -320,7 +341,7 @@ def run_b200(args) -> None:
         "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
                                    f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},
-    }), flush=True)
+    })
 
 
 def main() -> None:
@@ -339,8 +360,7 @@ def main() -> None:
     # torch is imported).
     if int(os.environ.get("RANK", "0")) == 0:
         os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its banner goes to stdout, which carries the one JSON line
-        os.environ["NCCL_DEBUG"] = "WARN"
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -62,6 +62,16 @@ def _linear(mod: nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = 
                       bias_lp=wcache.cast(mod, "b", mod.bias, compute_dtype()))
 
 
+def _bias_sum32(*mods) -> torch.Tensor:
+    """fp32 sum of the biases of ``mods`` (``None`` entries skipped), cached on the first module."""
+    mods = [m for m in mods if m is not None]
+    if len(mods) == 1:
+        return _bias32(mods[0])
+    srcs = tuple(m.bias for m in mods)
+    return wcache.get(mods[0], "b32+" + ",".join(str(id(m)) for m in mods[1:]), srcs,
+                      lambda: sum(p.detach().float() for p in srcs).contiguous())
+
+
 def _conv1x1_weight(mod: nn.Conv2d, cols: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """(C_out, C_in) 16-bit GEMM weight of a 1x1 convolution, or the contiguous copy of its input columns [lo, hi)."""
     if cols is None:
@@ -83,10 +93,8 @@ def _conv1x1_as_linear(mod: nn.Conv2d, tokens: torch.Tensor, extra_bias: Optiona
     elif extra_bias is None:
         b, b_lp = _bias32(mod), wcache.cast(mod, "b", mod.bias, compute_dtype())
     else:
-        b = wcache.get(mod, "b32+", (mod.bias, extra_bias.bias),
-                       lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).contiguous())
-        b_lp = wcache.get(mod, "b+" + str(compute_dtype()), (mod.bias, extra_bias.bias),
-                          lambda: (mod.bias.detach().float() + extra_bias.bias.detach().float()).to(compute_dtype()).contiguous())
+        b = _bias_sum32(mod, *([extra_bias] if isinstance(extra_bias, nn.Module) else extra_bias))
+        b_lp = wcache.get(mod, "b+lp", (b,), lambda: b.to(compute_dtype()))
     return ops.linear(tokens, w, b, residual, out=out, bias_lp=b_lp)
 
 
@@ -212,13 +220,20 @@ class Transformer2DModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(channels, heads, channels // heads, cross_attention_dim)])
         self.proj_out = nn.Conv2d(channels, channels, 1)
 
-    def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, ehs: torch.Tensor, x_carries_out_bias: bool = False) -> torch.Tensor:
+        """``x_carries_out_bias``: the producer of ``x`` (the resnet before this block, whose only consumers are the norm and
+        the residual add below) has already added ``proj_out.bias`` to it.  The norm then takes ``-proj_out.bias`` as its
+        per-channel additive term and ``proj_out(t) + x`` is one GEMM accumulating onto ``x`` - no bias / residual pass."""
         b, c, h, w = x.shape
-        t = _tokens(_gn(self.norm, x, silu=False))                  # free view (channels-last)
+        shift = None
+        if x_carries_out_bias:
+            shift = wcache.get(self.proj_out, "-b32", (self.proj_out.bias,), lambda: -self.proj_out.bias.detach().float())
+            shift = shift.view(1, -1).expand(b, -1)
+        t = _tokens(_gn(self.norm, x, silu=False, chan_add=shift))   # free view (channels-last)
         t = _conv1x1_as_linear(self.proj_in, t)
         for blk in self.transformer_blocks:
             t = blk(t, ehs)
-        return _image(_conv1x1_as_linear(self.proj_out, t, residual=_tokens(x)), h, w)
+        return _image(_conv1x1_as_linear(self.proj_out, t, residual=_tokens(x), bias=not x_carries_out_bias), h, w)
 
 
 class ResnetBlock2D(nn.Module):
@@ -232,14 +247,15 @@ class ResnetBlock2D(nn.Module):
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
-    def forward(self, x: torch.Tensor, temb_term: Optional[torch.Tensor], skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, temb_term: Optional[torch.Tensor], skip: Optional[torch.Tensor] = None,
+                carry_bias: Optional[nn.Module] = None) -> torch.Tensor:
         """``temb_term`` = time_emb_proj(silu(emb)) + conv1.bias as fp32 (B, cout) (``UNet2DConditionModel.time_terms``):
         folded into norm2's input by the GN kernel.  No convolution adds its own bias: conv1's rides on ``temb_term``,
         conv2's on the residual add (or on the shortcut GEMM's epilogue).
 
         ``skip``: the block input is ``cat([x, skip], dim=1)`` (up path).  The concatenation is never written: norm1 reads
         both tensors (``dadd_groupnorm_cat_fwd``) and the 1x1 shortcut is two accumulating GEMMs over the two halves of
-        its weight."""
+        its weight.  ``carry_bias``: a module whose bias is added to the output on top (``Transformer2DModel.forward``)."""
         if skip is not None and not ops.group_norm_cat_supported(x, skip, self.norm1.num_groups):
             x, skip = torch.cat([x, skip], dim=1), None
         if skip is not None:
@@ -253,14 +269,15 @@ class ResnetBlock2D(nn.Module):
             temb_term = _bias32(self.conv1).view(1, -1).expand(x.shape[0], -1)
         h = _conv_nobias(self.conv2, _gn(self.norm2, h, silu=True, chan_add=temb_term))
         if self.conv_shortcut is None:
-            return ops.bias_residual(h, x, _bias32(self.conv2), out=h)
+            return ops.bias_residual(h, x, _bias_sum32(self.conv2, carry_bias), out=h)
         # out = shortcut(x) + conv2(h) + both biases: the 1x1 shortcut GEMM takes h as the residual of its epilogue; with a
         # skip tensor it is two accumulating GEMMs over the two halves of its weight (the second adds onto the first in place)
         b, c1, hh, ww = x.shape
         if skip is None:
-            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2, residual=_tokens(h))
+            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=(self.conv2, carry_bias), residual=_tokens(h))
         else:
-            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=self.conv2, cols=(0, c1), residual=_tokens(h))
+            out = _conv1x1_as_linear(self.conv_shortcut, _tokens(x), extra_bias=(self.conv2, carry_bias), cols=(0, c1),
+                                     residual=_tokens(h))
             out = _conv1x1_as_linear(self.conv_shortcut, _tokens(skip), cols=(c1, c1 + skip.shape[1]), residual=out, bias=False,
                                      out=out)
         return _image(out, hh, ww)
@@ -428,22 +445,25 @@ class UNet2DConditionModel(nn.Module):
         skips = [x]
         for blk in self.down_blocks:
             for j, res in enumerate(blk.resnets):
-                x = res(x, terms[id(res)])
-                if len(blk.attentions) > 0:
-                    x = blk.attentions[j](x, ehs)
+                # a resnet followed by a Transformer2D hands it proj_out's bias in advance (see Transformer2DModel.forward)
+                attn = blk.attentions[j] if len(blk.attentions) > 0 else None
+                x = res(x, terms[id(res)], carry_bias=attn.proj_out if attn is not None else None)
+                if attn is not None:
+                    x = attn(x, ehs, x_carries_out_bias=True)
                 skips.append(x)
             if blk.downsamplers is not None:
                 x = blk.downsamplers[0](x)
                 skips.append(x)
         mb = self.mid_block
-        x = mb.resnets[0](x, terms[id(mb.resnets[0])])
-        x = mb.attentions[0](x, ehs)
+        x = mb.resnets[0](x, terms[id(mb.resnets[0])], carry_bias=mb.attentions[0].proj_out)
+        x = mb.attentions[0](x, ehs, x_carries_out_bias=True)
         x = mb.resnets[1](x, terms[id(mb.resnets[1])])
         for blk in self.up_blocks:
             for j, res in enumerate(blk.resnets):
-                x = res(x, terms[id(res)], skip=skips.pop())
-                if len(blk.attentions) > 0:
-                    x = blk.attentions[j](x, ehs)
+                attn = blk.attentions[j] if len(blk.attentions) > 0 else None
+                x = res(x, terms[id(res)], skip=skips.pop(), carry_bias=attn.proj_out if attn is not None else None)
+                if attn is not None:
+                    x = attn(x, ehs, x_carries_out_bias=True)
             if blk.upsamplers is not None:
                 x = blk.upsamplers[0](x)
         x = _gn(self.conv_norm_out, x, silu=True)
