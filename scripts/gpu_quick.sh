@@ -1,8 +1,14 @@
-mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout=300 -p no:cacheprovider -k "layernorm or groupnorm_expanded" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/summary.txt
-timeout 1200 python -m pytest tests/test_gpu_model.py -m gpu -q -x --timeout=900 -p no:cacheprovider -s > gpurun_out/pytest_model.log 2>&1; echo "pytest model rc=$?" >> gpurun_out/summary.txt
-for P in 2 8; do
-timeout 600 python scripts/profile_step.py --patients $P > gpurun_out/profile_p$P.log 2>&1; echo "profile P=$P rc=$?" >> gpurun_out/summary.txt
-done
-timeout 600 python bench.py --steps 2 > gpurun_out/bench_r22.json 2> gpurun_out/bench_r22.err; echo "bench rc=$?" >> gpurun_out/summary.txt
-cat gpurun_out/summary.txt; tail -3 gpurun_out/pytest_gpu.log; grep -E "rel err|PSNR|passed|failed" gpurun_out/pytest_model.log | tail -22; cat gpurun_out/profile_p2.log gpurun_out/profile_p8.log; wc -l gpurun_out/bench_r22.json; cut -c1-330 gpurun_out/bench_r22.json
+mkdir -p gpurun_out; rm -f gpurun_out/kb_gn4.log
+run() { echo "== $1" >> gpurun_out/kb_gn4.log; env $1 timeout 300 python scripts/kbench.py --kernel gn --batch 104 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l); print(d['kernel'], d['us_cold'], d['us_hot_l2'], d['frac_hbm_peak'])
+    except Exception: print(l.strip()[:200])" >> gpurun_out/kb_gn4.log; }
+run "X=1"
+run "DADD_GN_THREADS=256 DADD_GN_SLAB_KB=48 DADD_GN_SMAX=16"
+run "DADD_GN_THREADS=256 DADD_GN_SLAB_KB=96 DADD_GN_SMAX=8"
+run "DADD_GN_THREADS=512 DADD_GN_SLAB_KB=48 DADD_GN_SMAX=16"
+run "DADD_GN_THREADS=384 DADD_GN_SLAB_KB=64 DADD_GN_SMAX=16"
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -p no:cacheprovider -k "groupnorm" > gpurun_out/pytest_gn.log 2>&1; echo "pytest default rc=$?" >> gpurun_out/kb_gn4.log
+DADD_GN_THREADS=256 DADD_GN_SLAB_KB=48 DADD_GN_SMAX=16 timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -p no:cacheprovider -k "groupnorm" > gpurun_out/pytest_gn16.log 2>&1; echo "pytest S16 rc=$?" >> gpurun_out/kb_gn4.log
+cat gpurun_out/kb_gn4.log; tail -3 gpurun_out/pytest_gn16.log
