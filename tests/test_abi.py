@@ -66,3 +66,25 @@ def test_missing_library_fails_loudly(lib, monkeypatch):
     monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libdadd_b200.so")
     with pytest.raises(lib.DaddError):
         lib.load()
+
+
+def test_argument_validation_of_the_newer_entry_points(lib):
+    """Every entry point validates shapes / alignment before touching CUDA, so the error channel is testable without a GPU."""
+    l = lib.load()
+    err = lambda: l.dadd_last_error().decode()
+    assert l.dadd_linear_supported(1024, 320, 320) == 1 and l.dadd_linear_supported(1024, 96, 320) == 0
+    assert l.dadd_linear_supported(1024, 320, 324) == 0                     # K % 8
+    assert l.dadd_linear_fwd(16, 16, None, None, 16, 128, 96, 320, 1, None) != 0 and "multiple of 160 or 256" in err()
+    assert l.dadd_linear_fwd(None, 16, None, None, 16, 128, 320, 320, 1, None) != 0 and "dadd_linear_fwd" in err()
+    assert l.dadd_ff_geglu_fwd(16, 16, 16, 16, 128, 320, 1000, 1, None) != 0 and "inner % 128" in err()
+    assert l.dadd_ff_geglu_fwd(16, 16, 16, 16, 128, 320, 1280, 0, None) != 0 and "dtype16_ok" in err()      # fp32 not taken
+    assert l.dadd_groupnorm_cat_supported(4, 640, 320, 1024, 32, 1) == 1
+    assert l.dadd_groupnorm_cat_supported(4, 644, 320, 1024, 32, 1) == 0    # C1 % 8
+    assert l.dadd_groupnorm_cat_supported(4, 640, 320, 1024, 32, 0) == 0    # fp32
+    assert l.dadd_groupnorm_cat_fwd(16, 644, 16, 320, 16, 16, None, 0, 16, 4, 1024, 32, 1e-5, 1, 1, None, 0, None) != 0
+    assert "dadd_groupnorm_cat_fwd" in err()
+    assert l.dadd_upsample_nearest2x_fwd(16, 16, 1, 8, 8, 12, 1, None) != 0 and "C % 8" in err()
+    assert l.dadd_quick_gelu_fwd(16, 16, 12, 1, None) != 0 and "n % 8" in err()
+    assert l.dadd_cross_attn_fwd(16, 320, 16, 16, 16, 320, 1, 8, 64, 40, 16, 3, 16, 0.1, 1, 2, None) != 0 and "impl = 2" in err()
+    assert l.dadd_add_layernorm_fwd(16, 16, None, 16, 16, 16, 16, 4, 320, 1e-5, 1, None) != 0            # sum_bias without sum_out
+    assert l.dadd_purifier_attn_fwd(16, 16, 16, 16, 1, 16, 100000, 768, 8, None) != 0 and "shared memory" in err()
