@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdadd_b200.so")
+LIB_PATH = os.environ.get("DADD_B200_LIB") or os.path.join(HERE, "libdadd_b200.so")      # (override: A/B builds of a kernel)
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 

@@ -357,11 +357,20 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
                 uint64_t acc[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[i] = pack_f2(0.0f, 0.0f);
+                // the exponents a = s * c - m * c are formed here, outside the exp2 phase: while a MUFU instruction dispatches
+                // (8 clk for 32 lanes) its warp cannot issue, so inside the phase every other instruction adds to the MUFU time
+                // one for one (per-phase timeline and what it implies: profiles/r01_attn_exp_phase.txt)
+#pragma unroll
+                for (int k = 0; k < BN_ / 2; ++k) {
+                    float a0, a1;
+                    unpack_f2(fma_f2(pack_f2(__uint_as_float(sr[2 * k]), __uint_as_float(sr[2 * k + 1])), cc, nb), a0, a1);
+                    sr[2 * k] = __float_as_uint(a0);
+                    sr[2 * k + 1] = __float_as_uint(a1);
+                }
                 DADD_TRACE_EVENT(q, s, 4);
                 named_sync(1 + q, 256);                               // my turn on the MUFU pipe
                 // (ptxas is free to start the exp2 stream before the barrier - measured best: a hard hand-over leaves one warp per
                 // scheduler, whose in-order issue sustains only ~2/3 of the MUFU rate)
-                const uint64_t ccx = cc;
                 DADD_TRACE_EVENT(q, s, 5);
                 // Software-pipelined in batches of 8: the exp2 of batch b are issued back to back while the results of batch
                 // b-1 (long in flight) are summed, converted and stored, so ONE warp per scheduler keeps the MUFU pipe busy.
@@ -373,7 +382,7 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
                     auto scaled = [&](int base, uint64_t (&a)[4]) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            a[k] = fma_f2(pack_f2(__uint_as_float(sr[base + 2 * k]), __uint_as_float(sr[base + 2 * k + 1])), ccx, nb);
+                            a[k] = pack_f2(__uint_as_float(sr[base + 2 * k]), __uint_as_float(sr[base + 2 * k + 1]));
                     };
                     // pair k of batch bt: MUFU, or the FMA-pipe polynomial for a fixed share of the pairs (a ragged tile runs
                     // the all-MUFU instance: its masked -inf scores must map to exactly 0)
@@ -407,6 +416,9 @@ self_attn_tc2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pprev[i] = pcur[i];
                         if ((bt & 3) == 0) tmem_st16(tP + (bt / 4 - 1) * 16, pk);   // 32 probabilities = 16 packed columns done
+                        if (bt == 4) DADD_TRACE_EVENT(q, s, 10);
+                        if (bt == 8) DADD_TRACE_EVENT(q, s, 11);
+                        if (bt == 12) DADD_TRACE_EVENT(q, s, 12);
                     }
                 };
                 if (POLY > 0 && !ragged) exp_phase(std::integral_constant<int, POLY>{});

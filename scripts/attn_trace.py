@@ -14,4 +14,4 @@ names = {0: "WG0", 1: "WG1", 2: "MMA"}
 for step in range(0, 26):
     for role in range(3):
         r = rows[role * 64 + step]
-        print(f"step {step:2d} {names[role]}: " + " ".join(f"{(v - t0) if v else -1:7d}" for v in r[:9]))
+        print(f"step {step:2d} {names[role]}: " + " ".join(f"{(v - t0) if v else -1:7d}" for v in r[:13]))
