@@ -8,29 +8,40 @@ namespace daddk {
 
 constexpr int LN_MAX_VEC = 8;  // 8 vectors x 8 elements x 32 lanes = C <= 2048
 
-// (optional residual add +) LayerNorm, one warp per row, R rows per warp in flight, the rows packed in registers.
+// (optional residual add +) LayerNorm.  A row is owned by LPR lanes (32, 16 or 8: C = 320 is 40 16-byte vectors, which 8 lanes
+// x 5 vectors cover exactly, where a full warp would leave 24 of its 64 slots empty), so a warp works on 32 / LPR rows at a time,
+// R such passes in flight, the rows packed in registers.
 //   s = x (+ y) rounded to T (written to sum_out when given, plus sum_bias[c] when given);  out = LayerNorm(s) * gamma + beta.
-// Exact two-pass mean / variance in fp32.  NV = ceil(C / 256) 16-byte vectors per lane.  All loads of the R rows are
-// issued before the first reduction: R * C * sizeof(T) bytes in flight per warp (the kernel is latency-bound otherwise).
-template <typename T, int NV, int R, bool ADD>
+// Exact two-pass mean / variance in fp32.  NV = ceil(C / (8 LPR)) 16-byte vectors per lane.  All loads are issued before the
+// first reduction: R * (32 / LPR) * C * sizeof(T) bytes in flight per warp (the kernel is latency-bound otherwise).
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T, int NV, int R, bool ADD, int LPR>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const T* __restrict__ yadd, T* __restrict__ sum_out,
                                                         const float* __restrict__ sum_bias,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         T* __restrict__ out, int64_t rows, int C, float eps) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    constexpr int G = 32 / LPR;                                  // rows per warp pass
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (R * G);
     if (row0 >= rows) return;
     const int nvec = C >> 3;
     Vec8<T> vx[R][NV], vy[ADD ? R : 1][ADD ? NV : 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (row0 + r < rows) {
+        const int64_t row = row0 + r * G + grp;
+        if (row < rows) {
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                const int iv = lane + j * 32;
+                const int iv = sub + j * LPR;
                 if (iv < nvec) {
-                    vx[r][j].load(x + (row0 + r) * C + (iv << 3));
-                    if constexpr (ADD) vy[r][j].load(yadd + (row0 + r) * C + (iv << 3));
+                    vx[r][j].load(x + row * C + (iv << 3));
+                    if constexpr (ADD) vy[r][j].load(yadd + row * C + (iv << 3));
                 }
             }
         }
@@ -38,13 +49,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
     const float inv_c = 1.0f / (float)C;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (row0 + r >= rows) break;
+        if (row0 + r * G >= rows) break;                         // warp-uniform: no row of this pass exists
+        const int64_t row = row0 + r * G + grp;
+        const bool live = row < rows;                            // (dead lanes carry zeros through the shuffles)
         float f[NV][8];
         float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int iv = lane + j * 32;
-            if (iv < nvec) {
+            const int iv = sub + j * LPR;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[j][i] = 0.0f;
+            if (live && iv < nvec) {
                 vx[r][j].unpack(f[j]);
                 if constexpr (ADD) {
                     float g[8];
@@ -63,9 +78,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                             for (int i = 0; i < 8; ++i) fb[i] = f[j][i] + cb[i];
                             Vec8<T> tb;
                             tb.pack(fb);
-                            tb.store(sum_out + (row0 + r) * C + (iv << 3));
+                            tb.store(sum_out + row * C + (iv << 3));
                         } else {
-                            t.store(sum_out + (row0 + r) * C + (iv << 3));
+                            t.store(sum_out + row * C + (iv << 3));
                         }
                     }
                     t.unpack(f[j]);                       // LayerNorm sees the rounded sum, like the unfused graph
@@ -74,12 +89,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                 for (int i = 0; i < 8; i += 2) { s0 += f[j][i]; s1 += f[j][i + 1]; }
             }
         }
-        const float mean = warp_sum(s0 + s1) * inv_c;
+        const float mean = group_sum<LPR>(s0 + s1) * inv_c;
         float q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int iv = lane + j * 32;
-            if (iv < nvec) {
+            const int iv = sub + j * LPR;
+            if (live && iv < nvec) {
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
                     const float d0 = f[j][i] - mean, d1 = f[j][i + 1] - mean;
@@ -88,11 +103,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                 }
             }
         }
-        const float rstd = rsqrtf(warp_sum(q0 + q1) * inv_c + eps);
+        const float rstd = rsqrtf(group_sum<LPR>(q0 + q1) * inv_c + eps);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int iv = lane + j * 32;
-            if (iv < nvec) {
+            const int iv = sub + j * LPR;
+            if (live && iv < nvec) {
                 const float4 g0 = *reinterpret_cast<const float4*>(gamma + (iv << 3));
                 const float4 g1 = *reinterpret_cast<const float4*>(gamma + (iv << 3) + 4);
                 const float4 b0 = *reinterpret_cast<const float4*>(beta + (iv << 3));
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                 for (int i = 0; i < 8; ++i) o[i] = (f[j][i] - mean) * rstd * g[i] + bb[i];
                 Vec8<T> t;
                 t.pack(o);
-                t.store(out + (row0 + r) * C + (iv << 3));
+                t.store(out + row * C + (iv << 3));
             }
         }
     }
@@ -113,25 +128,28 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
 template <typename T, bool ADD>
 static int launch_layernorm(const T* x, const T* yadd, T* sum_out, const float* sum_bias, const float* gamma, const float* beta, T* out,
                             int64_t rows, int C, float eps, cudaStream_t s) {
-    const int nv = (C / 8 + 31) / 32;
+    const int nvec = C / 8;
+    const int nv = (nvec + 31) / 32;
     const int wpb = 8;
-#define DADD_LN(NVV, RR)                                                                                                  \
+#define DADD_LN(NVV, RR, LL)                                                                                              \
     do {                                                                                                                  \
-        const int64_t per_block = (int64_t)wpb * RR;                                                                      \
-        layernorm_kernel<T, NVV, RR, ADD><<<(unsigned)((rows + per_block - 1) / per_block), wpb * 32, 0, s>>>(            \
-            x, yadd, sum_out, sum_bias, gamma, beta, out, rows, C, eps);                                                            \
+        const int64_t per_block = (int64_t)wpb * RR * (32 / LL);                                                          \
+        layernorm_kernel<T, NVV, RR, ADD, LL><<<(unsigned)((rows + per_block - 1) / per_block), wpb * 32, 0, s>>>(        \
+            x, yadd, sum_out, sum_bias, gamma, beta, out, rows, C, eps);                                                  \
         return launched("dadd_layernorm_fwd");                                                                            \
     } while (0)
     if constexpr (sizeof(T) == 2) {
-        if (nv <= 1) DADD_LN(1, 4);
-        if (nv == 2) DADD_LN(2, 4);
-        if (nv == 3) DADD_LN(3, 2);
-        if (nv <= 5) DADD_LN(5, 1);
-        DADD_LN(8, 1);
+        if (nvec == 40) DADD_LN(5, 1, 8);               // C = 320: 8 lanes x 5 vectors per row, 4 rows per warp
+        if (nvec == 80) DADD_LN(5, 1, 16);              // C = 640: 16 lanes x 5 vectors, 2 rows per warp
+        if (nv <= 1) DADD_LN(1, 4, 32);
+        if (nv == 2) DADD_LN(2, 4, 32);
+        if (nv == 3) DADD_LN(3, 2, 32);
+        if (nv <= 5) DADD_LN(5, 1, 32);
+        DADD_LN(8, 1, 32);
     } else {
-        if (nv <= 1) DADD_LN(1, 2);
-        if (nv <= 3) DADD_LN(3, 1);
-        DADD_LN(8, 1);
+        if (nv <= 1) DADD_LN(1, 2, 32);
+        if (nv <= 3) DADD_LN(3, 1, 32);
+        DADD_LN(8, 1, 32);
     }
 #undef DADD_LN
 }
