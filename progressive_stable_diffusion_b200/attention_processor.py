@@ -12,7 +12,6 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 
 from . import ops, wcache
 

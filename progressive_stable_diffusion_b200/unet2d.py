@@ -9,11 +9,14 @@ is kept.  Execution is B200-first:
 
 * activations are bf16 **channels-last** end to end: convolutions hit cuDNN's NHWC tensor-core kernels (off-path by the
   north-star), the Transformer2D entry/exit permutes are free views and the 1x1 ``proj_in/out`` are plain GEMMs;
-* every GroupNorm(+SiLU) is one ``dadd_groupnorm_fwd`` call, with the resnet time-embedding add folded into ``norm2``;
+* every GroupNorm(+SiLU) is one ``dadd_groupnorm_fwd`` call, with the resnet time-embedding add folded into ``norm2``; the
+  skip concatenations of the up path are never written (``dadd_groupnorm_cat_fwd`` + a shortcut GEMM split over its halves);
 * no convolution adds its own bias (PyTorch would launch a broadcasting add per conv): conv1's bias rides on the
-  time-embedding row, conv2's on the fused residual add (``dadd_bias_residual_fwd``) or the shortcut GEMM's epilogue;
-* LayerNorm is fused with the residual add that feeds it (``dadd_add_layernorm_fwd``), GEGLU is one kernel;
-  self/cross attention are the processors' fused kernels;
+  time-embedding row, conv2's on the fused residual add (``dadd_bias_residual_fwd``) or the shortcut GEMM;
+* LayerNorm is fused with the residual add that feeds it (``dadd_add_layernorm_fwd``); the feed-forward projection and its
+  GEGLU gate are one tcgen05 GEMM (``dadd_ff_geglu_fwd``); the biases of ``ff.net[2]`` and ``proj_out`` ride on the
+  residuals they are added to, so both projections are single accumulating GEMMs; self/cross attention are the
+  processors' fused kernels;
 * the 22 ``time_emb_proj`` matrices are one stacked fp32 GEMM per forward (or one per sampling call, see
   ``precompute_time_terms``), and nothing in ``forward`` synchronises, so a whole step can be captured in a CUDA graph.
 """
