@@ -241,3 +241,25 @@ def test_sample_progressions_from_pixels_encodes_each_patient_once():
         a = sample_progressions(module, pixels, src, 3, 2, DEV, init_latents=noise, decode=False)
         b = sample_progressions(module, tokens, src, 3, 2, DEV, init_latents=noise, decode=False)
     assert a.shape == (6, 4, 32, 32) and torch.equal(a, b) and torch.isfinite(a).all()
+
+
+def test_progression_512_end_to_end():
+    """BASELINE config 5 through the public API: 512x512 (64x64 latents) progression with the graph-replayed sampler and the
+    VAE decode (GroupNorm flat passes with many chunks, 4096-token self-attention); finite images of the right shape, and the
+    graph replay equals eager stepping bit for bit."""
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import sample_progressions
+    cfg = P.default_config()
+    cfg.dataset.image_size = 512
+    torch.manual_seed(5)
+    module = P.DiffusionModuleWithIP(cfg).to(DEV).eval()
+    g = torch.Generator().manual_seed(14)
+    tokens = torch.randn(1, 16, 768, generator=g)
+    noise = torch.randn(1, 4, 64, 64, generator=g)
+    src = torch.tensor([1.0])
+    with torch.no_grad():
+        imgs = sample_progressions(module, tokens, src, 2, 2, DEV, init_latents=noise)
+        lat_g = sample_progressions(module, tokens, src, 2, 2, DEV, init_latents=noise, decode=False)
+        lat_e = sample_progressions(module, tokens, src, 2, 2, DEV, init_latents=noise, decode=False, use_graph=False)
+    assert imgs.shape == (2, 3, 512, 512) and torch.isfinite(imgs).all() and 0.0 <= imgs.min() and imgs.max() <= 1.0
+    assert torch.equal(lat_g, lat_e)
