@@ -279,6 +279,19 @@ def run_b200(args) -> None:
         torch.cuda.synchronize(dev)
         xa_s = e0.elapsed_time(e1) / 1e3 / reps
         xa_bytes = qx[0].numel() * 2 * 2 + kc.numel() * 2 * 2
+        # ---- residual add + LayerNorm N=1024, C=320 (reads x and r, writes the sum and the norm); operands rotate through
+        # more than the L2 ----
+        lnw, lnb = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+        for i in range(3):
+            ops.add_layer_norm(qx[i], qx[(i + 1) % 3], lnw, lnb, 1e-5)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for i in range(reps):
+            ops.add_layer_norm(qx[i % 3], qx[(i + 1) % 3], lnw, lnb, 1e-5)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ln_s = e0.elapsed_time(e1) / 1e3 / reps
+        ln_bytes = qx[0].numel() * 2 * 4
 
         if args.profile_step:      # one eager denoising step between cudaProfilerStart/Stop (ncu --profile-from-start off)
             eng.state.zero_()
@@ -338,6 +351,9 @@ def run_b200(args) -> None:
                                 "achieved": xa_bytes / xa_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                 "frac": xa_bytes / xa_s / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("cross_attn"),
                                 "us_per_launch": xa_s * 1e6},
+        "roofline_add_layernorm": {"kernel": "residual add + LayerNorm (N=1024, C=320) at the bench batch", "bound": "hbm",
+                                   "achieved": ln_bytes / ln_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": ln_bytes / ln_s / 1e9 / pk["hbm_gbs"], "traffic": None, "us_per_launch": ln_s * 1e6},
         "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
                                    f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},
