@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(NTHREADS, NP == 1 ? 2 : 1)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, T* __restrict__ o,
                      int64_t o_stride, int B, int H, int N, int d,
-                     const float* __restrict__ gates, float scale_log2e) {
+                     const float* __restrict__ gates, float scale_log2e, int group_walk) {
     constexpr int L = SEG * NSEG;
     constexpr uint32_t TMEM_COLS = NP == 1 ? 256 : 512;
     constexpr uint32_t FMT = std::is_same_v<T, __nv_bfloat16> ? 1u : 0u;
@@ -86,7 +86,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nq = (N + BM - 1) / BM;
     const int items = nq * H * B;
-    const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // Item order.  group_walk (long sequences, many heads per CTA): a CTA walks whole (sample, head) groups - group = CTA + j *
+    // CTAs, its nq tiles one after the other - so that the tiles reuse the K_cat / V_cat already sitting in a stage while the
+    // neighbouring CTAs work on the other heads of the sample at the same time and share the 128-byte lines of Q / O in L2.
+    // Otherwise item = CTA + i * CTAs (best balance when there are few groups or few tiles per group).
+    const int groups = H * B;
+    const int my_items = group_walk ? ((groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * nq
+                                    : (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto item_of = [&](int i) {
+        return group_walk ? ((int)blockIdx.x + (i / nq) * (int)gridDim.x) * nq + i % nq : (int)blockIdx.x + i * (int)gridDim.x;
+    };
     const int ksteps = (d + 15) >> 4;
 
     if (tid == 0) {
@@ -113,17 +122,23 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     if (warp == 8) {
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer: ring of whole items
+            int held[STAGES];                                    // (sample, head) whose K_cat / V_cat a stage holds
+            for (int s = 0; s < STAGES; ++s) held[s] = -1;
             for (int i = 0; i < my_items; ++i) {
-                const int item = (int)blockIdx.x + i * (int)gridDim.x;
-                const int t = item % nq, h = (item / nq) % H, b = item / (nq * H);
+                const int item = item_of(i);
+                const int t = item % nq, bh = item / nq, h = bh % H, b = bh / H;
                 const int st = i % STAGES;
                 mbar_wait(&bars->empty[st], ((i / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&bars->full[st], STAGE_BYTES);
+                const bool kv = held[st] != bh;
+                held[st] = bh;
+                mbar_expect_tx(&bars->full[st], kv ? STAGE_BYTES : NP * Q_PANEL);
                 unsigned char* base = sStage + st * STAGE_BYTES;
                 for (int p = 0; p < NP; ++p) {
                     tma_load_4d(smem_u32(base + p * Q_PANEL), &tq, &bars->full[st], p * 64, t * BM, h, b);
-                    tma_load_4d(smem_u32(base + NP * Q_PANEL + p * KV_PANEL), &tk, &bars->full[st], p * 64, 0, h, b);
-                    tma_load_4d(smem_u32(base + NP * (Q_PANEL + KV_PANEL) + p * KV_PANEL), &tv, &bars->full[st], p * 64, 0, h, b);
+                    if (kv) {
+                        tma_load_4d(smem_u32(base + NP * Q_PANEL + p * KV_PANEL), &tk, &bars->full[st], p * 64, 0, h, b);
+                        tma_load_4d(smem_u32(base + NP * (Q_PANEL + KV_PANEL) + p * KV_PANEL), &tv, &bars->full[st], p * 64, 0, h, b);
+                    }
                 }
             }
         }
@@ -184,7 +199,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         for (int s = 0; s < NSEG; ++s) gate[s] = gates[s];
         int k = 0;
         for (int i = q; i < my_items; i += 2, ++k) {
-            const int item = (int)blockIdx.x + i * (int)gridDim.x;
+            const int item = item_of(i);
             const int t = item % nq, h = (item / nq) % H, b = item / (nq * H);
             mbar_wait(&bars->s_full[q], k & 1);
             fence_after();
@@ -313,10 +328,13 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
     const size_t smem = (size_t)STAGES * NP * (128 * 128 + 2 * L * 128) + (NP == 1 ? 2 * 128 * 128 : 0) + sizeof(Bars<STAGES>) + 1024;
     const int items = ((N + BM - 1) / BM) * H * B;
     const int ctas = (NP == 1 ? 2 : 1) * num_sms();
-    const int grid = items < ctas ? items : ctas;
+    const int nq = (N + BM - 1) / BM, groups = H * B;
+    // measured on B200 (profiles/r01_cross_attn_kv_reuse.txt): the group walk wins at N = 1024 with >= 2 groups per CTA
+    const int group_walk = (nq >= 4 && groups >= 2 * ctas) ? 1 : 0;
+    const int grid = group_walk ? ctas : (items < ctas ? items : ctas);
     auto kern = cross_attn_tc_kernel<T, NP, SEG, NSEG, STAGES>;
     if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cross_attn_tc smem")) return 2;
-    kern<<<grid, NTHREADS, smem, s>>>(tq, tk, tv, to, (T*)o, o_stride, B, H, N, d, gates, scale * 1.4426950408889634f);
+    kern<<<grid, NTHREADS, smem, s>>>(tq, tk, tv, to, (T*)o, o_stride, B, H, N, d, gates, scale * 1.4426950408889634f, group_walk);
     return launched("dadd_cross_attn_fwd(tcgen05)");
 }
 
