@@ -449,7 +449,8 @@ def _cross_ref(q, k, v, gates, heads, seg, nseg):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
 @pytest.mark.parametrize("seg,nseg", [(16, 3), (16, 2), (32, 1)])
-@pytest.mark.parametrize("n,d,b", [(1024, 40, 3), (256, 80, 5), (128, 64, 2), (200, 40, 2), (4096, 40, 1), (333, 128, 1), (1024, 40, 40)])
+@pytest.mark.parametrize("n,d,b", [(1024, 40, 3), (256, 80, 5), (128, 64, 2), (200, 40, 2), (4096, 40, 1), (333, 128, 1), (1024, 40, 40),
+                                   (1024, 40, 80), (640, 64, 90)])      # >= 2 (sample, head) groups per CTA: the group-walk order
 def test_cross_attention_core_tcgen05_vs_mma_vs_fp32(n, d, b, seg, nseg, dtype):
     """The tcgen05 kernel (N >= 128), the mma.sync kernel and the fp32 reference on the same 16-bit operands; q is a strided
     view (row stride 2C) as when it aliases a fused projection, and b = 40 gives every persistent CTA several items."""
