@@ -210,6 +210,27 @@ class DiffusionModuleWithIP(nn.Module):
                 out[name] = {"anat_gate": proc.anat_gate.item(), "dis_gate": proc.dis_gate.item()}
         return out
 
+    # ------------------------------------------------------------------ reference :289-313 (host-side pieces of the training path)
+    @property
+    def device(self) -> torch.device:
+        return self.alphas_cumprod.device
+
+    def _sample_timesteps(self, batch_size: int) -> Tensor:
+        return torch.randint(0, self.diff_cfg.num_train_timesteps, (batch_size,), device=self.device, dtype=torch.long)
+
+    def _q_sample(self, x0: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+        """Forward diffusion x_t = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise (reference :299-303)."""
+        sqrt_ab = torch.sqrt(self.alphas_cumprod[t]).view(-1, 1, 1, 1)
+        sqrt_1m = torch.sqrt(1.0 - self.alphas_cumprod[t]).view(-1, 1, 1, 1)
+        return sqrt_ab * x0 + sqrt_1m * noise
+
+    def _min_snr_weight(self, t: Tensor) -> Tensor:
+        """Min-SNR-gamma loss weight min(snr, gamma) / (snr + 1e-8) (reference :305-313)."""
+        if not getattr(getattr(self.cfg, "training", SimpleNamespace()), "use_min_snr_weighting", True):
+            return torch.ones_like(t, dtype=torch.float32, device=self.device)
+        snr = self.snr_values[t]
+        return torch.minimum(snr, torch.tensor(self.diff_cfg.min_snr_gamma, device=snr.device)) / (snr + 1e-8)
+
     def training_step(self, *args, **kwargs):
         raise NotImplementedError("training (backward kernels + DDP) is the next tier (SURVEY.md 8f, row f1)")
 

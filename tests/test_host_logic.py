@@ -160,3 +160,17 @@ def test_load_from_checkpoint_reads_the_ema_layout(tmp_path, module):
     assert torch.equal(sd[key_u], ema[key_u]) and torch.equal(sd[key_p], ema[key_p])
     assert loaded.image_encoder is None            # no image_encoder.* keys in this checkpoint -> front end not built
     assert set(sd) == set(module.state_dict())
+
+
+def test_q_sample_and_min_snr_weight(module):
+    """Host-side pieces of the training path (reference diffusion_module_ip.py:289-313) against their closed forms."""
+    g = torch.Generator().manual_seed(21)
+    x0, noise = torch.randn(3, 4, 8, 8, generator=g), torch.randn(3, 4, 8, 8, generator=g)
+    t = torch.tensor([0, 500, 999])
+    ab = module.alphas_cumprod[t].view(-1, 1, 1, 1)
+    torch.testing.assert_close(module._q_sample(x0, t, noise), ab.sqrt() * x0 + (1 - ab).sqrt() * noise)
+    snr = module.alphas_cumprod[t] / (1 - module.alphas_cumprod[t] + 1e-8)
+    torch.testing.assert_close(module._min_snr_weight(t), torch.clamp(snr, max=module.diff_cfg.min_snr_gamma) / (snr + 1e-8))
+    assert module._min_snr_weight(t)[0] < 1e-2 and abs(module._min_snr_weight(t)[2].item() - 1.0) < 1e-4   # high SNR clipped, low SNR -> snr / (snr + 1e-8) ~ 1
+    ts = module._sample_timesteps(64)
+    assert ts.dtype == torch.long and ts.shape == (64,) and 0 <= int(ts.min()) and int(ts.max()) < 1000
