@@ -28,7 +28,9 @@ extern "C" {
 #define DADD_LAYOUT_NCHW 0 /* x[b][c][hw]  (the reference's tensors)                     */
 #define DADD_LAYOUT_NHWC 1 /* x[b][hw][c]  (channels-last; what the B200 UNet runs in)    */
 
-/* ABI version of this header (bumped on any signature change; currently 8). */
+/* ABI version of this header (bumped on any signature change).  The host binding refuses a library whose
+ * dadd_abi_version() differs from the DADD_ABI_VERSION it was written against. */
+#define DADD_ABI_VERSION 9
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -54,16 +56,18 @@ int dadd_ddim_step(float* x, const void* eps_cond, const void* eps_uncond /* nul
 /* Same update with the per-step scalars read on the device, so that one captured CUDA graph can be replayed
  * for every step of the schedule.  coef_table is [n_steps][8] fp32 rows
  *   {sqrt_ab_t, sqrt_1mab_t, sqrt_ab_prev, eps_coef, sigma, is_last (0/1), 0, 0}
- * and step_state is int32[2] = {current step, next step} maintained by dadd_step_begin(). */
+ * and step_state is int32[2] = {current step, next step} maintained by dadd_step_begin().  The step index is clamped to
+ * [0, n_steps) on the device: a replay past the end of the schedule cannot read outside the tables. */
 int dadd_ddim_step_table(float* x, const void* eps_cond, const void* eps_uncond /* nullable */, int eps_dtype,
-                         float guidance, const float* coef_table, const int32_t* step_state,
+                         float guidance, const float* coef_table, const int32_t* step_state, int n_steps,
                          const float* noise /* nullable; [n_steps][n] when given */, float clamp, int64_t n,
                          void* stream);
 
 /* First node of a per-step graph: step_state[0] = step_state[1]; step_state[1] += 1; and copy row
  * step_state[0] of a [n_steps][row_len] table (the hoisted per-step time-embedding projections of all
- * resnets) into `row_out`.  `table` may be NULL (row_len = 0). */
-int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64_t row_bytes, void* stream);
+ * resnets) into `row_out` (row index clamped to [0, n_steps)).  `table` may be NULL
+ * (row_len = 0). */
+int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64_t row_bytes, int n_steps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional per-(sample,channel) additive term, + optional SiLU).

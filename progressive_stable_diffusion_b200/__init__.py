@@ -5,7 +5,7 @@ kernels in ``libdadd_b200.so`` reached through the C ABI of ``include/dadd_b200.
 """
 
 from . import _lib  # noqa: F401
-from .attention_processor import AttnProcessor2_0, compute_dtype, set_compute_dtype  # noqa: F401
+from .attention_processor import AttnProcessor2_0, DEFAULT_COMPUTE_DTYPE, compute_dtype, set_compute_dtype  # noqa: F401
 from .attention_processor_base import (OrdinalIPAttnProcessor2_0, get_frequency_mode_for_block,  # noqa: F401
                                        set_ordinal_ip_attention_processors)
 from .attention_processor_routing_gates import (SplitInjectionAttentionProcessor, get_block_type,  # noqa: F401
@@ -18,7 +18,7 @@ from .unet import OrdinalUNet, UNetConfig  # noqa: F401
 from .vae import SDVAE  # noqa: F401
 
 __all__ = [
-    "AttnProcessor2_0", "compute_dtype", "set_compute_dtype", "OrdinalIPAttnProcessor2_0", "SplitInjectionAttentionProcessor", "get_block_type",
+    "AttnProcessor2_0", "DEFAULT_COMPUTE_DTYPE", "compute_dtype", "set_compute_dtype", "OrdinalIPAttnProcessor2_0", "SplitInjectionAttentionProcessor", "get_block_type",
     "get_frequency_mode_for_block", "set_ordinal_ip_attention_processors", "set_split_injection_processors",
     "DiffusionIPConfig", "DiffusionModuleWithIP", "default_config", "load_config", "FeaturePurifier",
     "AdditiveOrdinalEmbedder", "OrdinalUNet", "UNetConfig", "SDVAE", "ImageEncoder", "ImageProjection", "ImageProjectionPlus",

@@ -14,11 +14,13 @@ LIB_PATH = os.environ.get("DADD_B200_LIB") or os.path.join(HERE, "libdadd_b200.s
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
+ABI_VERSION = 9          # == DADD_ABI_VERSION of include/dadd_b200.h that SIGNATURES below was written against
+
 # name -> argtypes; mirrors include/dadd_b200.h one to one (tests/test_abi.py checks header <-> table <-> .so)
 SIGNATURES = {
     "dadd_ddim_step": [_P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _P, _F, _I, _L, _P],
-    "dadd_ddim_step_table": [_P, _P, _P, _I, _F, _P, _P, _P, _F, _L, _P],
-    "dadd_step_begin": [_P, _P, _P, _L, _P],
+    "dadd_ddim_step_table": [_P, _P, _P, _I, _F, _P, _P, _I, _P, _F, _L, _P],
+    "dadd_step_begin": [_P, _P, _P, _L, _I, _P],
     "dadd_groupnorm_workspace_bytes": [_I, _I, _I, _I, _I],
     "dadd_groupnorm_fwd": [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P, _L, _P],
     "dadd_groupnorm_cat_supported": [_I, _I, _I, _I, _I, _I],
@@ -58,11 +60,15 @@ def load() -> ctypes.CDLL:
             "(no CPU / eager fallback). Build them with `python -m progressive_stable_diffusion_b200.build`."
         )
     lib = ctypes.CDLL(LIB_PATH)
+    lib.dadd_abi_version.restype = c_int
+    have = int(lib.dadd_abi_version())
+    if have != ABI_VERSION:      # the .so is git-ignored and survives checkouts: never call it through mismatched signatures
+        raise DaddError(f"{LIB_PATH} has ABI version {have}, this binding needs {ABI_VERSION}: rebuild it with "
+                        "`python -m progressive_stable_diffusion_b200.build --force`")
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = c_int64 if name.endswith("_bytes") else c_int
-    lib.dadd_abi_version.restype = c_int
     lib.dadd_last_error.restype = c_char_p
     lib.dadd_launch_count.restype = c_int64
     lib.dadd_reset_launch_count.restype = None

@@ -44,17 +44,17 @@ class OrdinalIPAttnProcessor2_0(nn.Module):
         if length % 16 != 0 or length > 64:
             raise NotImplementedError(f"dadd_cross_attn_fwd takes 16..64 condition tokens in multiples of 16, got {length}")
 
-        def build(w: torch.Tensor):
-            def fn():
-                p = F.linear(ehs.detach().to(w.dtype), w)
-                b, l, c = p.shape
-                return p.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(compute_dtype()).contiguous()
-            return fn
+        def project(w: torch.Tensor) -> torch.Tensor:
+            p = F.linear(ehs.detach().to(w.dtype), w)
+            b, l, c = p.shape
+            return p.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(compute_dtype()).contiguous()
 
-        src = (ehs, attn.to_k.weight, attn.to_v.weight)
-        tag = f"kv:{ehs.data_ptr()}:{tuple(ehs.shape)}"
-        return (wcache.get(self, "k" + tag, src, build(attn.to_k.weight)),
-                wcache.get(self, "v" + tag, src, build(attn.to_v.weight)), length)
+        cache = self.__dict__.get("_cond_cache")
+        if cache is None:
+            cache = self.__dict__["_cond_cache"] = wcache.CondCache()
+        k_cat, v_cat = cache.get(ehs, (), (attn.to_k.weight, attn.to_v.weight),
+                                 lambda: (project(attn.to_k.weight), project(attn.to_v.weight)))
+        return k_cat, v_cat, length
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None, *args, **kwargs):

@@ -74,23 +74,24 @@ class SplitInjectionAttentionProcessor(nn.Module):
         n = self._segments()
         with_delta = self.delta_scale != 0.0
         ehs = encoder_hidden_states
-        sources = (ehs, attn.to_k.weight, attn.to_v.weight, self.to_k_dis.weight, self.to_v_dis.weight)
+        sources = (attn.to_k.weight, attn.to_v.weight, self.to_k_dis.weight, self.to_v_dis.weight)
 
-        def build(wa: torch.Tensor, wd: torch.Tensor):
-            def fn():
-                e = ehs.detach().to(wa.dtype)
-                dis, anat = e[:, :n, :], e[:, n:n + self.num_image_tokens, :]
-                parts = [F.linear(dis, wd), F.linear(anat, wa)]
-                if with_delta:
-                    parts.append(F.linear(e[:, -self.num_delta_tokens:, :], wd))
-                cat = torch.cat(parts, dim=1)                                   # (B, L, C)
-                b, l, c = cat.shape
-                return cat.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(compute_dtype()).contiguous()
-            return fn
+        def project(wa: torch.Tensor, wd: torch.Tensor) -> torch.Tensor:
+            e = ehs.detach().to(wa.dtype)
+            dis, anat = e[:, :n, :], e[:, n:n + self.num_image_tokens, :]
+            parts = [F.linear(dis, wd), F.linear(anat, wa)]
+            if with_delta:
+                parts.append(F.linear(e[:, -self.num_delta_tokens:, :], wd))
+            cat = torch.cat(parts, dim=1)                                   # (B, L, C)
+            b, l, c = cat.shape
+            return cat.view(b, l, attn.heads, c // attn.heads).permute(0, 2, 1, 3).to(compute_dtype()).contiguous()
 
-        tag = f"kv{int(with_delta)}:{ehs.data_ptr()}:{tuple(ehs.shape)}"
-        k_cat = wcache.get(self, "k" + tag, sources, build(attn.to_k.weight, self.to_k_dis.weight))
-        v_cat = wcache.get(self, "v" + tag, sources, build(attn.to_v.weight, self.to_v_dis.weight))
+        cache = self.__dict__.get("_cond_cache")
+        if cache is None:
+            cache = self.__dict__["_cond_cache"] = wcache.CondCache()
+        k_cat, v_cat = cache.get(ehs, (with_delta,), sources,
+                                 lambda: (project(attn.to_k.weight, self.to_k_dis.weight),
+                                          project(attn.to_v.weight, self.to_v_dis.weight)))
         return k_cat, v_cat, (3 if with_delta else 2)
 
     def gate_vector(self) -> torch.Tensor:

@@ -33,9 +33,11 @@ template <typename T, bool TABLE>
 __global__ void __launch_bounds__(256) ddim_kernel(float* __restrict__ x, const T* __restrict__ ec,
                                                    const T* __restrict__ eu, float g, DdimCoef c,
                                                    const float* __restrict__ table, const int32_t* __restrict__ state,
-                                                   const float* __restrict__ noise, float clampv, int64_t n) {
+                                                   int n_steps, const float* __restrict__ noise, float clampv, int64_t n) {
     if (TABLE) {
-        const int s = state[0];
+        // a replay beyond the schedule must not index past the tables: it re-applies the last row (and is reported by
+        // the host wrapper, which knows how many replays it queued)
+        const int s = min(max(state[0], 0), n_steps - 1);
         const float* r = table + (int64_t)s * 8;
         c.sa = r[0]; c.so = r[1]; c.sap = r[2]; c.ec = r[3]; c.sigma = r[4];
         c.is_last = r[5] != 0.0f;
@@ -48,10 +50,11 @@ __global__ void __launch_bounds__(256) ddim_kernel(float* __restrict__ x, const 
 }
 
 __global__ void step_begin_kernel(int32_t* state, const uint4* __restrict__ table, uint4* __restrict__ row_out,
-                                  int64_t row_vecs) {
+                                  int64_t row_vecs, int n_steps) {
     const int cur = state[1];
+    const int row = min(max(cur, 0), n_steps - 1);       // never read past the table (see ddim_kernel)
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < row_vecs; i += blockDim.x) row_out[i] = table[(int64_t)cur * row_vecs + i];
+    for (int64_t i = threadIdx.x; i < row_vecs; i += blockDim.x) row_out[i] = table[(int64_t)row * row_vecs + i];
     if (threadIdx.x == 0) {
         state[0] = cur;
         state[1] = cur + 1;
@@ -104,7 +107,7 @@ using namespace daddk;
 
 extern "C" {
 
-int dadd_abi_version(void) { return 8; }
+int dadd_abi_version(void) { return DADD_ABI_VERSION; }
 const char* dadd_last_error(void) { return g_last_error; }
 int64_t dadd_launch_count(void) { return g_launches.load(); }
 void dadd_reset_launch_count(void) { g_launches.store(0); }
@@ -119,29 +122,29 @@ int dadd_ddim_step(float* x, const void* eps_cond, const void* eps_uncond, int e
     DdimCoef c{sqrt_ab_t, sqrt_1mab_t, sqrt_ab_prev, eps_coef, sigma, is_last};
     cudaStream_t s = (cudaStream_t)stream;
     DADD_DISPATCH_ANY(eps_dtype, T, (ddim_kernel<T, false><<<grid_for(n, 256), 256, 0, s>>>(
-                                        x, (const T*)eps_cond, (const T*)eps_uncond, guidance, c, nullptr, nullptr, noise, clampv, n)));
+                                        x, (const T*)eps_cond, (const T*)eps_uncond, guidance, c, nullptr, nullptr, 1, noise, clampv, n)));
     return launched("dadd_ddim_step");
 }
 
 int dadd_ddim_step_table(float* x, const void* eps_cond, const void* eps_uncond, int eps_dtype, float guidance,
-                         const float* coef_table, const int32_t* step_state, const float* noise, float clampv,
-                         int64_t n, void* stream) {
-    DADD_REQUIRE(x && eps_cond && coef_table && step_state && n >= 0, "dadd_ddim_step_table");
+                         const float* coef_table, const int32_t* step_state, int n_steps, const float* noise,
+                         float clampv, int64_t n, void* stream) {
+    DADD_REQUIRE(x && eps_cond && coef_table && step_state && n >= 0 && n_steps >= 1, "dadd_ddim_step_table");
     DADD_REQUIRE(dtype_ok(eps_dtype), "dadd_ddim_step_table");
     if (n == 0) return 0;
     DdimCoef c{};
     cudaStream_t s = (cudaStream_t)stream;
     DADD_DISPATCH_ANY(eps_dtype, T, (ddim_kernel<T, true><<<grid_for(n, 256), 256, 0, s>>>(
-                                        x, (const T*)eps_cond, (const T*)eps_uncond, guidance, c, coef_table, step_state, noise, clampv, n)));
+                                        x, (const T*)eps_cond, (const T*)eps_uncond, guidance, c, coef_table, step_state, n_steps, noise, clampv, n)));
     return launched("dadd_ddim_step_table");
 }
 
-int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64_t row_bytes, void* stream) {
-    DADD_REQUIRE(step_state != nullptr, "dadd_step_begin");
+int dadd_step_begin(int32_t* step_state, const void* table, void* row_out, int64_t row_bytes, int n_steps, void* stream) {
+    DADD_REQUIRE(step_state != nullptr && n_steps >= 1, "dadd_step_begin");
     DADD_REQUIRE(row_bytes % 16 == 0, "dadd_step_begin");
     DADD_REQUIRE(row_bytes == 0 || (table && row_out), "dadd_step_begin");
     step_begin_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(step_state, (const uint4*)table, (uint4*)row_out,
-                                                            row_bytes / 16);
+                                                            row_bytes / 16, n_steps);
     return launched("dadd_step_begin");
 }
 

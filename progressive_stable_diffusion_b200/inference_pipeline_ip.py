@@ -15,13 +15,14 @@ What is different underneath:
 from __future__ import annotations
 
 import os
+from collections import OrderedDict
 
 from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor
 
-from . import ops
+from . import ops, wcache
 from .attention_processor import compute_dtype
 from .attention_processor_base import OrdinalIPAttnProcessor2_0
 from .attention_processor_routing_gates import SplitInjectionAttentionProcessor
@@ -105,6 +106,9 @@ def _cudnn_flags():
     return torch.backends.cudnn.flags(enabled=True, benchmark=CUDNN_BENCHMARK)
 
 
+MAX_ENGINES = int(os.environ.get("DADD_MAX_ENGINES", "4"))     # least-recently-used engines beyond this are freed
+
+
 class ProgressionEngine:
     """Static buffers + one captured step graph for a fixed (batch, latent size, steps, eta, cfg, pathways) signature."""
 
@@ -117,24 +121,55 @@ class ProgressionEngine:
         h = module.cfg.dataset.image_size // 8
         c = module.cfg.model.latent_channels
         dim = module.cfg.model.conditioning_dim
-        self.timesteps, table = ddim_schedule(module.alphas_cumprod, T, sampling_steps, eta)
-        self.coef = table.to(device)
         self.x = torch.zeros(batch, c, h, h, device=device, dtype=torch.float32)
         self.ehs = torch.zeros(batch, tokens, dim, device=device, dtype=torch.float32)
         self.ehs_u = torch.zeros_like(self.ehs) if do_cfg else None
+        wcache.pin(self.ehs)                     # the K/V projected from these buffers are read by the captured graph:
+        if self.ehs_u is not None:               # their cache entries live as long as the buffers
+            wcache.pin(self.ehs_u)
         self.state = torch.zeros(2, device=device, dtype=torch.int32)
         self.noise = (torch.zeros(sampling_steps, batch * c * h * h, device=device, dtype=torch.float32)
                       if eta != 0.0 else None)
-        unet = module.unet.unet
-        self.terms_table = unet.time_terms(self.timesteps.to(device)).contiguous()      # (S, sum C_out) fp32, hoisted
+        self.coef = self.terms_table = None
+        self._build_tables()
         self.terms_row = torch.zeros(1, self.terms_table.shape[1], device=device, dtype=torch.float32)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
         self.launches_per_step = 0
+        self.weight_stamp = self._weights_stamp()
+
+    def _build_tables(self) -> None:
+        """DDIM coefficient table and the hoisted time-embedding rows (S, sum C_out), refreshed IN PLACE when they exist."""
+        m = self.module
+        self.timesteps, table = ddim_schedule(m.alphas_cumprod, m.diff_cfg.num_train_timesteps, self.steps, self.eta)
+        terms = m.unet.unet.time_terms(self.timesteps.to(self.device)).contiguous()
+        if self.coef is None:
+            self.coef, self.terms_table = table.to(self.device), terms
+        else:
+            self.coef.copy_(table)
+            self.terms_table.copy_(terms)
+
+    def _weights_stamp(self) -> Tuple:
+        """(address, version) of every parameter and buffer the step reads: UNet + processors and the noise schedule."""
+        m = self.module
+        ts = list(m.unet.parameters()) + list(m.unet.buffers()) + [m.alphas_cumprod]
+        return tuple((t.data_ptr(), t._version, t.dtype) for t in ts)
+
+    def _revalidate_weights(self) -> None:
+        """``load_state_dict`` / an EMA swap / ``module.to(...)`` after the first capture: the derived 16-bit / fused weights
+        (``wcache``) are refreshed only when the Python forward runs and the tables above were computed from the old
+        weights, so a replay would mix old and new.  Rebuild the tables in place and drop the graph; the next ``run``
+        re-captures after an eager warm-up that refreshes every derived tensor."""
+        stamp = self._weights_stamp()
+        if stamp != self.weight_stamp:
+            self._build_tables()
+            self.graph = None
+            self.launches_per_step = 0
+            self.weight_stamp = stamp
 
     # one denoising step on the static buffers
     def _step(self) -> None:
-        ops.step_begin_(self.state, self.terms_table, self.terms_row)
+        ops.step_begin_(self.state, self.terms_table, self.terms_row, self.steps)
         m = self.module
         with _cudnn_flags():
             eps_c = m(self.x, None, self.ehs, time_terms=self.terms_row)
@@ -142,13 +177,17 @@ class ProgressionEngine:
         ops.ddim_step_table_(self.x, eps_c, eps_u, self.guidance, self.coef, self.state, self.noise, 4.0)
 
     def _refresh_kv(self) -> None:
-        """Re-project the condition tokens into the (address-stable) per-site K/V caches for the current conditioning."""
+        """Everything a replay reads that the Python forward would otherwise refresh: the condition tokens re-projected into
+        the (address-stable) per-site K/V caches, and each routing processor's device gate vector
+        (dis_gate, anat_gate, delta_scale) - a steer-scale sweep on one engine changes only that vector."""
         for mod in self.module.unet.unet.modules():
             proc = getattr(mod, "processor", None)
             if isinstance(proc, (SplitInjectionAttentionProcessor, OrdinalIPAttnProcessor2_0)):
                 proc.project_kv(mod, self.ehs)
                 if self.do_cfg:
                     proc.project_kv(mod, self.ehs_u)
+                if isinstance(proc, SplitInjectionAttentionProcessor):
+                    proc.gate_vector()
 
     def _capture(self) -> None:
         from . import _lib
@@ -181,6 +220,7 @@ class ProgressionEngine:
             self.noise.zero_()
             if step_noise is not None:
                 self.noise[: step_noise.shape[0]].copy_(step_noise.reshape(step_noise.shape[0], -1))
+        self._revalidate_weights()
         self._refresh_kv()
         if self.graph is None and (self.use_graph or self.launches_per_step == 0):
             self._capture()
@@ -200,13 +240,16 @@ class ProgressionEngine:
 
 def _engine_for(module, batch: int, sampling_steps: int, eta: float, do_cfg: bool, guidance_scale: float, tokens: int,
                 device: torch.device, steer_scale: float, use_graph: bool = True) -> ProgressionEngine:
-    cache: Dict = module.__dict__.setdefault("_b200_engines", {})
+    cache: "OrderedDict" = module.__dict__.setdefault("_b200_engines", OrderedDict())
     key = (batch, sampling_steps, float(eta), do_cfg, float(guidance_scale) if do_cfg else 0.0, tokens, str(device),
            steer_scale != 0.0, use_graph, module.cfg.dataset.image_size, str(compute_dtype()))
     eng = cache.get(key)
     if eng is None:
         eng = ProgressionEngine(module, batch, sampling_steps, eta, do_cfg, guidance_scale, tokens, device, use_graph)
         cache[key] = eng
+        while len(cache) > MAX_ENGINES:          # each engine owns a captured graph and its private memory pool
+            cache.popitem(last=False)
+    cache.move_to_end(key)
     return eng
 
 

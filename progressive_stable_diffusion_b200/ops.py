@@ -61,23 +61,31 @@ def ddim_step_table_(x: torch.Tensor, eps_cond: torch.Tensor, eps_uncond: Option
                      clamp: float = 4.0) -> torch.Tensor:
     _cuda(x, eps_cond, eps_uncond, coef_table, step_state, noise)
     assert x.dtype == torch.float32 and x.is_contiguous() and eps_cond.is_contiguous()
-    assert coef_table.dtype == torch.float32 and coef_table.shape[-1] == 8 and coef_table.is_contiguous()
+    assert coef_table.dtype == torch.float32 and coef_table.dim() == 2 and coef_table.shape[-1] == 8 and coef_table.is_contiguous()
     assert step_state.dtype == torch.int32 and step_state.numel() == 2
+    assert eps_cond.numel() == x.numel() and (eps_uncond is None or (eps_uncond.is_contiguous() and eps_uncond.dtype == eps_cond.dtype
+                                                                     and eps_uncond.numel() == x.numel()))
+    n_steps = coef_table.shape[0]
+    assert noise is None or (noise.dtype == torch.float32 and noise.is_contiguous() and noise.numel() == n_steps * x.numel())
     _lib.check(_lib.load().dadd_ddim_step_table(x.data_ptr(), eps_cond.data_ptr(), _ptr(eps_uncond), _dt(eps_cond),
-                                                guidance, coef_table.data_ptr(), step_state.data_ptr(), _ptr(noise),
+                                                guidance, coef_table.data_ptr(), step_state.data_ptr(), n_steps, _ptr(noise),
                                                 clamp, x.numel(), _stream()), "dadd_ddim_step_table")
     return x
 
 
-def step_begin_(step_state: torch.Tensor, table: Optional[torch.Tensor] = None, row_out: Optional[torch.Tensor] = None) -> None:
+def step_begin_(step_state: torch.Tensor, table: Optional[torch.Tensor] = None, row_out: Optional[torch.Tensor] = None,
+                n_steps: Optional[int] = None) -> None:
+    """Advance the device-side step counter and stage row ``step`` of ``table`` (n_steps, row) into ``row_out``."""
     _cuda(step_state, table, row_out)
     row_bytes = 0
     if table is not None:
-        assert table.is_contiguous() and row_out.is_contiguous() and table.dtype == row_out.dtype
+        assert table.dim() == 2 and table.is_contiguous() and row_out.is_contiguous() and table.dtype == row_out.dtype
         row_bytes = row_out.numel() * row_out.element_size()
         assert table[0].numel() == row_out.numel()
-    _lib.check(_lib.load().dadd_step_begin(step_state.data_ptr(), _ptr(table), _ptr(row_out), row_bytes, _stream()),
-               "dadd_step_begin")
+        assert n_steps is None or n_steps == table.shape[0]
+        n_steps = table.shape[0]
+    _lib.check(_lib.load().dadd_step_begin(step_state.data_ptr(), _ptr(table), _ptr(row_out), row_bytes,
+                                           1 if n_steps is None else int(n_steps), _stream()), "dadd_step_begin")
 
 
 # --------------------------------------------------------------------------------------------- norms

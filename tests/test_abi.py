@@ -53,7 +53,7 @@ def test_ctypes_table_covers_the_header(lib):
 
 def test_abi_version_and_error_channel(lib):
     l = lib.load()
-    assert l.dadd_abi_version() == 8
+    assert l.dadd_abi_version() == lib.ABI_VERSION
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = l.dadd_groupnorm_fwd(None, None, None, None, 0, None, 1, 320, 64, 32, 1e-5, 1, 1, 1, None, 0, None)
     assert rc != 0 and b"dadd_groupnorm_fwd" in l.dadd_last_error()

@@ -409,7 +409,7 @@ def compute(request):
     import progressive_stable_diffusion_b200 as P
     P.set_compute_dtype(request.param)
     yield request.param
-    P.set_compute_dtype(torch.bfloat16)
+    P.set_compute_dtype(P.DEFAULT_COMPUTE_DTYPE)
 
 
 @pytest.mark.parametrize("case", cases.PROCESSOR_CASES, ids=lambda c: c["name"])

@@ -3,11 +3,13 @@
 Gates: eps max relative error <= 2e-2 (16-bit kernels vs fp32 oracle), final decoded images
 PSNR >= 40 dB, gate / token indexing bit-exact.
 
-Precision note (profiles/r01_precision_experiment.txt): with random-init, non-contractive weights the 50-step trajectory
-amplifies per-step eps error; every bf16-operand implementation - stock PyTorch autocast included - ends at 26-30 dB, fp16
-operands (same tensor-core rate; the reference's own mixed-precision dtype) at 42-45 dB.  So the eps gate is asserted for
-both compute dtypes, the 50-step PSNR >= 40 dB gate for fp16, and bf16's 50-step PSNR is asserted against the measured
-bf16 floor.
+The package's DEFAULT compute dtype - the one bench.py measures - is fp16 (the reference's own mixed-precision dtype,
+evaluation_pipeline.py:943) and is held to EVERY gate: eps <= 2e-2 (asserted at 4e-3), PSNR >= 40 dB after 8 and after 50
+steps, CFG trajectory <= 3e-2.  bf16 is an opt-in alternative (``set_compute_dtype(torch.bfloat16)``): it meets the eps gate
+(the only one BASELINE.md states for bf16 operands) but, with random-init non-contractive weights, the 50-step trajectory
+amplifies its 8x larger per-step rounding to 26-30 dB for ANY bf16-operand implementation, stock PyTorch autocast included
+(profiles/r01_precision_experiment.txt).  Its trajectory tests therefore check graph == eager and the measured bf16 floor,
+and are NOT a claim of the 40 dB gate.
 """
 
 import math
@@ -20,8 +22,14 @@ pytestmark = pytest.mark.gpu
 from oracle import conditioning, sampler, unet as ounet, weights  # noqa: E402
 
 DEV = "cuda:0"
+DEFAULT_DTYPE = torch.float16          # == progressive_stable_diffusion_b200.DEFAULT_COMPUTE_DTYPE (asserted below)
 TOL_EPS = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
 PSNR_MIN = 40.0
+
+
+def test_default_dtype_is_the_one_held_to_every_gate():
+    import progressive_stable_diffusion_b200 as P
+    assert P.DEFAULT_COMPUTE_DTYPE == DEFAULT_DTYPE == P.compute_dtype()
 
 
 def rel_err(a, ref):
@@ -49,7 +57,7 @@ def compute(request):
     import progressive_stable_diffusion_b200 as P
     P.set_compute_dtype(request.param)
     yield request.param
-    P.set_compute_dtype(torch.bfloat16)
+    P.set_compute_dtype(P.DEFAULT_COMPUTE_DTYPE)
 
 
 def _split(state):
@@ -114,8 +122,8 @@ def test_progression_matches_oracle_and_psnr(models, compute):
     assert torch.equal(lat, lat_eager), "graph replay and eager stepping must agree bit for bit"
     print(f"8 steps gain={gain:.2f} {compute}: latent rel err {rel_err(lat, lat_ref):.4g}, PSNR(oracle decoder) {p_lat:.1f} dB, "
           f"PSNR(product decoder) {p_full:.1f} dB")
-    assert p_lat >= (PSNR_MIN if compute == torch.float16 else 36.0), p_lat
-    assert p_full >= (PSNR_MIN if compute == torch.float16 else 36.0) - 3.0, p_full
+    assert p_lat >= (PSNR_MIN if compute == DEFAULT_DTYPE else 36.0), p_lat
+    assert p_full >= (PSNR_MIN if compute == DEFAULT_DTYPE else 33.0), p_full
 
 
 def test_full_50_step_progression_psnr(models, compute):
@@ -137,11 +145,11 @@ def test_full_50_step_progression_psnr(models, compute):
         p_full = psnr(_latents_to_images(module, lat), img_ref)
     print(f"50 steps {compute}: latent rel err {rel_err(lat, lat_ref):.4g}, PSNR(oracle decoder) {p_lat:.1f} dB, "
           f"PSNR(product decoder) {p_full:.1f} dB")
-    if compute == torch.float16:
-        assert p_lat >= PSNR_MIN, p_lat
-        assert p_full >= PSNR_MIN - 2.0, p_full
+    if compute == DEFAULT_DTYPE:
+        assert p_lat >= PSNR_MIN, p_lat      # the north-star gate, on the dtype the benchmark runs
+        assert p_full >= PSNR_MIN, p_full
     else:
-        assert p_lat >= 24.0, p_lat          # the bf16 floor every bf16-operand implementation hits (see module docstring)
+        assert p_lat >= 24.0, p_lat          # opt-in bf16: the floor every bf16-operand implementation hits (module docstring)
 
 
 def test_baseline_mode_with_cfg(compute):
@@ -162,7 +170,8 @@ def test_baseline_mode_with_cfg(compute):
         lat = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, guidance_scale=2.0, init_latents=noise)
     e = rel_err(lat, lat_ref)
     print(f"baseline+CFG latent rel err {compute}: {e:.4g}")
-    assert e <= (0.2 if compute == torch.bfloat16 else 0.03), e
+    # default dtype: a parity bound; opt-in bf16: 4 CFG steps (guidance 2 doubles the eps error) of 1.2e-2-per-step rounding
+    assert e <= (0.03 if compute == DEFAULT_DTYPE else 0.15), e
 
 
 def test_eta_sampling_uses_reference_rng_order(models):
@@ -263,3 +272,81 @@ def test_progression_512_end_to_end():
         lat_e = sample_progressions(module, tokens, src, 2, 2, DEV, init_latents=noise, decode=False, use_graph=False)
     assert imgs.shape == (2, 3, 512, 512) and torch.isfinite(imgs).all() and 0.0 <= imgs.min() and imgs.max() <= 1.0
     assert torch.equal(lat_g, lat_e)
+
+
+def test_steer_scale_sweep_reuses_one_engine(models, compute):
+    """evaluation sweeps call the sampler with several steer scales (evaluation_pipeline.py:1274).  All non-zero
+    scales share one captured engine; the scale reaches the device through each processor's gate vector, which must be
+    refreshed before every replay - the second scale used to produce the first scale's images."""
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import _ddim_sample_ip
+    module, _, gain, _ = models
+    if gain != 1.0:
+        pytest.skip("one weight set is enough")
+    n, steps = 2, 3
+    noise, img = _inputs(n, seed=21)
+    target, source = torch.tensor([0.5, 3.0]), torch.zeros(n)
+    out = {}
+    for steer in (3.0, 1.0, 3.0):
+        g = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, steer_scale=steer, init_latents=noise)
+        e = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, steer_scale=steer, init_latents=noise, use_graph=False)
+        assert torch.equal(g, e), steer
+        out.setdefault(steer, g)
+        assert torch.equal(out[steer], g)
+    assert not torch.equal(out[3.0], out[1.0])
+    # an in-place change of the routing gates reaches the replay as well
+    proc = next(p for p in module.unet.unet.attn_processors.values() if hasattr(p, "anat_gate"))
+    old = proc.anat_gate.clone()
+    proc.anat_gate.fill_(0.37)
+    try:
+        g = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, steer_scale=3.0, init_latents=noise)
+        e = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, steer_scale=3.0, init_latents=noise, use_graph=False)
+        assert torch.equal(g, e) and not torch.equal(g, out[3.0])
+    finally:
+        proc.anat_gate.copy_(old)
+
+
+def test_weight_update_reaches_a_captured_engine(compute):
+    """load_state_dict after the first capture (an EMA swap, a new checkpoint) must not leave the graph
+    replaying stale derived weights / time-embedding rows."""
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import _ddim_sample_ip
+    sa = weights.make_module_state(seed=7, with_vae=False)
+    sb = weights.make_module_state(seed=8, with_vae=False)
+    module = P.DiffusionModuleWithIP(P.default_config(), build_vae=False)
+    module.load_state_dict(sa, strict=True)
+    module.to(DEV).eval()
+    n, steps = 2, 3
+    noise, img = _inputs(n, seed=22)
+    target, source = torch.tensor([0.0, 2.0]), torch.ones(n)
+    kw = dict(steer_scale=3.0, init_latents=noise)
+    a_graph = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, **kw)
+    module.load_state_dict(sb, strict=True)
+    b_graph = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, **kw)
+    b_eager = _ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, use_graph=False, **kw)
+    assert torch.equal(b_graph, b_eager) and not torch.equal(a_graph, b_graph)
+    module.load_state_dict(sa, strict=True)
+    assert torch.equal(_ddim_sample_ip(module, target, source, img.to(DEV), steps, DEV, **kw), a_graph)
+
+
+def test_eager_calls_with_recycled_conditioning_addresses(models, compute):
+    """two different conditionings of the same shape, the first freed before the second is built (the caching
+    allocator then reuses its address), must each get their own K/V projections on the eager path."""
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import _prepare_conditioning, _set_delta_scale_on_processors
+    module, _, gain, _ = models
+    if gain != 1.0:
+        pytest.skip("one weight set is enough")
+    _, img = _inputs(1, seed=23)
+    x = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(24)).to(DEV)
+    t = torch.tensor([500], device=DEV)
+    _set_delta_scale_on_processors(module, 3.0)
+    src = torch.zeros(1, device=DEV)
+
+    def eps_for(label):
+        cond = _prepare_conditioning(module, torch.tensor([label], device=DEV), src, img.to(DEV))
+        return module(x, t, cond), cond.data_ptr()
+
+    with torch.no_grad():
+        e0, p0 = eps_for(0.0)
+        e3, p3 = eps_for(3.0)          # `cond` of the first call is dead: same shape, typically the same address
+        e0b, _ = eps_for(0.0)
+    assert torch.equal(e0, e0b) and not torch.equal(e0, e3), (p0, p3)

@@ -174,3 +174,57 @@ def test_q_sample_and_min_snr_weight(module):
     assert module._min_snr_weight(t)[0] < 1e-2 and abs(module._min_snr_weight(t)[2].item() - 1.0) < 1e-4   # high SNR clipped, low SNR -> snr / (snr + 1e-8) ~ 1
     ts = module._sample_timesteps(64)
     assert ts.dtype == torch.long and ts.shape == (64,) and 0 <= int(ts.min()) and int(ts.max()) < 1000
+
+
+def test_cond_cache_is_tied_to_the_tensor_object_not_its_address():
+    """an address-keyed K/V cache served a previous conditioning's projections to a new tensor that the allocator
+    placed at the same address.  Entries now follow the tensor object: they die with it, rebuild IN PLACE when it (or a
+    weight) is modified, transient conditionings are bounded by a small LRU and pinned (engine) ones are never evicted."""
+    import gc
+    from progressive_stable_diffusion_b200 import wcache
+    cache = wcache.CondCache(max_transient=2)
+    w = torch.ones(4, 4)
+    calls = []
+
+    def build_for(c):
+        def build():
+            calls.append(1)
+            return (c @ w, c * 2.0)
+        return build
+
+    a = torch.full((2, 4), 1.0)
+    k1, v1 = cache.get(a, (True,), (w,), build_for(a))
+    k1b, _ = cache.get(a, (True,), (w,), build_for(a))
+    assert k1b is k1 and len(calls) == 1                       # hit
+    a.add_(1.0)                                                # in-place update of the conditioning -> same storage, new values
+    k2, v2 = cache.get(a, (True,), (w,), build_for(a))
+    assert k2 is k1 and len(calls) == 2 and torch.equal(k2, a @ w)
+    w.mul_(2.0)                                                # weight update -> rebuilt in place too
+    k3, _ = cache.get(a, (True,), (w,), build_for(a))
+    assert k3 is k1 and len(calls) == 3 and torch.equal(k3, a @ w)
+    ptr = a.data_ptr()
+    del a, k1, k1b, k2, k3, v1, v2
+    gc.collect()
+    assert len(cache.entries) == 0                             # the entry died with its tensor
+    b = torch.full((2, 4), 5.0)                                # may or may not land on `ptr`: either way it must be a miss
+    kb, _ = cache.get(b, (True,), (w,), build_for(b))
+    assert len(calls) == 4 and torch.equal(kb, b @ w), ptr
+    # LRU of transient tensors; a pinned tensor's entry survives any number of them
+    pinned = torch.zeros(2, 4)
+    wcache.pin(pinned)
+    kp, _ = cache.get(pinned, (True,), (w,), build_for(pinned))
+    keep = [torch.full((2, 4), float(i)) for i in range(5)]
+    for t in keep:
+        cache.get(t, (True,), (w,), build_for(t))
+    alive = {k[0] for k in cache.entries}
+    assert id(pinned) in alive and len(cache.entries) == 3 and {id(keep[-1]), id(keep[-2])} <= alive
+    assert cache.get(pinned, (True,), (w,), build_for(pinned))[0] is kp
+
+
+def test_binding_refuses_a_library_of_another_abi(monkeypatch):
+    from progressive_stable_diffusion_b200 import _lib
+    _lib.load()
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "ABI_VERSION", _lib.ABI_VERSION + 1)
+    with pytest.raises(_lib.DaddError, match="ABI version"):
+        _lib.load()

@@ -65,3 +65,46 @@ def test_sampler_last_step_returns_clamped_x0_and_shapes():
     shapes = ounet.attention_shapes(32)
     assert [(c, n, d) for _, c, n, d in shapes].count((320, 1024, 40)) == 5
     assert [(c, n, d) for _, c, n, d in shapes].count((1280, 16, 160)) == 1
+
+
+# Published facts about the un-vendored dependency's checkpoint (CompVis/stable-diffusion-v1-4, diffusers layout) that any
+# restatement of its graph must reproduce exactly: the SD-1.x UNet2DConditionModel has 859 520 964 parameters in 686 tensors
+# (SURVEY.md section 2.1 quotes 859.5 M), the AutoencoderKL decoder 49 490 179 in 138 (+ post_quant_conv: 4*4 + 4 = 20 in 2).
+SD1X_UNET_PARAMS, SD1X_UNET_TENSORS = 859_520_964, 686
+SD1X_VAE_DECODER_PARAMS, SD1X_VAE_DECODER_TENSORS = 49_490_179, 138
+DADD_PROCESSOR_PARAMS = 2 * 768 * (5 * 320 + 5 * 640 + 6 * 1280)      # to_k_dis + to_v_dis of the 16 cross-attention sites
+
+
+def _count(state, prefix, exclude=()):
+    items = [(k, v) for k, v in state.items() if k.startswith(prefix) and not any(e in k for e in exclude)]
+    return sum(v.numel() for _, v in items), len(items)
+
+
+def test_unpinned_oracle_graphs_have_the_public_sd1x_shape():
+    """The UNet / VAE-decoder oracle restates an absent dependency (parity unpinned, oracle/unet.py header).  This pins its
+    SHAPE to the public checkpoint: exact parameter and tensor counts, the A.6 key families, and the same for the product
+    module (whose state dict must be loadable from a diffusers-layout checkpoint key for key)."""
+    import progressive_stable_diffusion_b200 as P
+    state = weights.make_module_state(seed=0)
+    assert _count(state, "unet.unet.", exclude=("processor",)) == (SD1X_UNET_PARAMS, SD1X_UNET_TENSORS)
+    proc_params, proc_tensors = _count({k: v for k, v in state.items() if "processor" in k}, "unet.unet.")
+    assert proc_tensors == 16 * 4 and proc_params == DADD_PROCESSOR_PARAMS + 16 * 2        # + anat_gate / dis_gate scalars
+    assert _count(state, "vae.vae.decoder.") == (SD1X_VAE_DECODER_PARAMS, SD1X_VAE_DECODER_TENSORS)
+    assert _count(state, "vae.vae.post_quant_conv.") == (20, 2)
+    module = P.DiffusionModuleWithIP(P.default_config())
+    sd = module.state_dict()
+    for prefix in ("unet.unet.", "vae.vae.", "ordinal_embedder.", "feature_purifier."):
+        want = {k: tuple(v.shape) for k, v in state.items() if k.startswith(prefix)}
+        got = {k: tuple(v.shape) for k, v in sd.items() if k.startswith(prefix)}
+        assert got == want, prefix
+    # key families of SURVEY.md A.6 and the per-site shapes of Appendix B.3
+    unet_keys = [k[len("unet.unet."):] for k in state if k.startswith("unet.unet.")]
+    fam = lambda s: sum(1 for k in unet_keys if s in k)
+    assert fam("time_emb_proj.weight") == 22 and fam("conv_shortcut.weight") == 14 and fam(".attn1.to_q.weight") == 16
+    assert fam("ff.net.0.proj.weight") == 16 and fam("downsamplers.0.conv.weight") == 3 and fam("upsamplers.0.conv.weight") == 3
+    for site, c in (("down_blocks.0.attentions.0", 320), ("down_blocks.1.attentions.1", 640), ("down_blocks.2.attentions.0", 1280),
+                    ("mid_block.attentions.0", 1280), ("up_blocks.1.attentions.2", 1280), ("up_blocks.2.attentions.0", 640),
+                    ("up_blocks.3.attentions.2", 320)):
+        base = f"unet.unet.{site}.transformer_blocks.0."
+        assert state[base + "attn2.to_k.weight"].shape == (c, 768) == state[base + "attn2.processor.to_v_dis.weight"].shape
+        assert state[base + "ff.net.0.proj.weight"].shape == (8 * c, c) and state[base + "ff.net.2.weight"].shape == (c, 4 * c)
