@@ -10,6 +10,14 @@ steps (max over ranks).  ``e2e``: the same through the public API ``sample_progr
 patients' CLIP-preprocessed structure images, encoded by the CLIP ViT-L/14 + resampler front end inside the call - and a
 device->host read of the finished images inside the timed region.  ``--impl reference`` times the reference's CPU path
 (the oracle port: same graph, PyTorch eager fp32 - diffusers is not installable here) on the box's host cores.
+
+After the headline the same run adds (each a separate object of the JSON line):
+``parity``   eps max relative error (B = 13, t = 999) and decoded-image PSNR of a 2-level x 50-step progression against the
+             CPU oracle, at the dtype the benchmark ran in (north-star gates: 2e-2 / 40 dB);
+``strong``   BASELINE config 2 read as STRONG scaling: 8 patients x 13 levels = 104 units in total, split over the ranks;
+``config4``  one guidance scale of the evaluation sweep (50 samples x 4 MES classes = 200 jobs, 50 steps) through
+             ``evaluation_pipeline.generate_all``, jobs sharded over the ranks;
+``config5``  the 512x512 stress progression, batch 16 in total split over the ranks.
 """
 
 from __future__ import annotations
@@ -27,6 +35,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 LEVELS, DDIM_STEPS, STEER = 13, 50, 3.0
+WORKLOAD = ("13 MES levels x 50 DDIM steps, lambda=3, 256x256, SD-1.x-shaped random-init weights, CFG off (routing gates), "
+            "eta=0, VAE decode included")
 UNET_GFLOP_PER_SAMPLE_STEP = 178.7
 SELF_ATTN_N, SELF_ATTN_D, SELF_ATTN_H = 1024, 40, 8
 
@@ -139,29 +149,82 @@ def cpu_reference_sample(batch: int, seed: int = 0):
 
 
 def run_reference(args) -> None:
+    """The reference's CPU path on the box's host cores.  One timed "step" = ONE UNet denoising step of one patient's 13-level
+    progression (B = 13) - a bounded sample of the 50 a progression takes; ``value`` scales it to the whole progression
+    (50 x mean step + one timed VAE decode) and ``ms_per_step`` is the timed unit itself."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     unet_step, decode, cores = cpu_reference_sample(LEVELS)
-    unet_step()                                                   # one untimed pass (each is ~10 s of host work)
     with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):               # untimed passes (each is ~1 s of host work)
+            unet_step()
         t_unet = [unet_step() for _ in range(args.steps)]
         t_dec = decode()
     per_step = statistics.mean(t_unet)
     progression_s = DDIM_STEPS * per_step + t_dec
     value = LEVELS / progression_s
-    sample = (f"{args.steps} timed UNet denoising step(s) at B=13 (oracle port, fp32 eager, {cores} threads) + 1 VAE decode at "
-              f"B=13; one 13x50 progression extrapolated as 50 x step + decode = {progression_s:.1f} s")
+    sample = (f"{args.steps} timed UNet denoising step(s) at B=13 (oracle port, fp32 eager, {cores} threads), mean {per_step * 1e3:.0f} ms, "
+              f"+ 1 VAE decode at B=13 ({t_dec:.2f} s); one 13x50 progression = 50 x step + decode = {progression_s:.1f} s")
     _emit({
         "impl": "reference", "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": progression_s * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "step_unit": "one UNet denoising step at B=13 (1/50 of a progression); value = 13 / (50 x step + decode)",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "13 MES levels x 50 DDIM steps, lambda=3, 256x256, SD-1.x-shaped random-init weights",
-                   "patients_per_gpu": 1, "levels": LEVELS, "ddim_steps": DDIM_STEPS},
+        "config": {"workload": WORKLOAD, "patients_per_gpu": args.patients, "levels": LEVELS, "ddim_steps": DDIM_STEPS,
+                   "images_per_step_per_gpu": args.patients * LEVELS,
+                   "note": "the CPU arm times one patient (13 images) at a time; img/s does not depend on how many patients queue"},
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
+
+
+def parity_block(dev, cdt) -> dict:
+    """North-star gates measured in this run at the benchmark's dtype, product vs the CPU oracle (the checker, never the thing
+    timed): eps max relative error for one patient's 13 levels at t = 999, and decoded-image PSNR after a 2-level x 50-step
+    progression (same weights, noise and conditioning on both sides)."""
+    import math
+    import torch
+    import progressive_stable_diffusion_b200 as P
+    from oracle import conditioning, sampler, unet as ounet, weights
+    from progressive_stable_diffusion_b200.inference_pipeline_ip import (_ddim_sample_ip, _latents_to_images, _prepare_conditioning,
+                                                                         _set_delta_scale_on_processors)
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = weights.make_module_state(seed=0)
+    module = P.DiffusionModuleWithIP(P.default_config())
+    module.load_state_dict(state, strict=True)
+    module.to(dev).eval()
+    uw, aw, pw, vw = (weights.sub_state(state, p) for p in ("unet.unet.", "ordinal_embedder.", "feature_purifier.", "vae.vae."))
+    g = torch.Generator().manual_seed(7)
+    noise = torch.randn(1, 4, 32, 32, generator=g)
+    tok1 = torch.randn(1, 16, 768, generator=g)
+    rel = lambda a, r: ((a.double().cpu() - r.double()).abs().max() / r.double().abs().max()).item()
+    with torch.no_grad():
+        # eps: one patient's 13 levels, first sampler position
+        tgt, src = torch.linspace(0, 3, LEVELS), torch.zeros(LEVELS)
+        tok = tok1.expand(LEVELS, -1, -1).contiguous()
+        x, t = noise.repeat(LEVELS, 1, 1, 1), torch.full((LEVELS,), 999, dtype=torch.long)
+        cond_ref = conditioning.prepare_conditioning(aw, pw, tgt, src, tok)
+        eps_ref = ounet.unet_forward(uw, x, t, cond_ref, ounet.CrossCfg(True, STEER))
+        cond = _prepare_conditioning(module, tgt.to(dev), src.to(dev), tok.to(dev))
+        _set_delta_scale_on_processors(module, STEER)
+        eps_err = rel(module(x.to(dev), t.to(dev), cond), eps_ref)
+        # images: 2 levels x 50 steps
+        tgt2, src2, tok2 = torch.tensor([0.75, 3.0]), torch.ones(2), tok1.expand(2, -1, -1).contiguous()
+        lat_ref = sampler.ddim_sample(uw, aw, pw, tgt2, src2, tok2, noise, sampling_steps=DDIM_STEPS, steer_scale=STEER)
+        img_ref = ounet.latents_to_images(vw, lat_ref)
+        lat = _ddim_sample_ip(module, tgt2, src2, tok2.to(dev), DDIM_STEPS, dev, steer_scale=STEER, init_latents=noise)
+        psnr = lambda a: (lambda mse: 99.0 if mse == 0 else 10.0 * math.log10(1.0 / mse))(((a.double().cpu() - img_ref.double()) ** 2).mean().item())
+        p_full, p_lat = psnr(_latents_to_images(module, lat)), psnr(ounet.latents_to_images(vw, lat.cpu()))
+    del module
+    torch.cuda.empty_cache()
+    return {"dtype": str(cdt).replace("torch.", ""), "eps_max_rel_err": eps_err, "eps_gate": 2e-2, "psnr_db": p_full,
+            "psnr_db_oracle_decoder": p_lat, "psnr_gate_db": 40.0, "latent_max_rel_err_50_steps": rel(lat, lat_ref),
+            "pass": bool(eps_err <= 2e-2 and p_full >= 40.0 and p_lat >= 40.0),
+            "how": "product (CUDA path, this dtype) vs oracle port (CPU fp32), same seeded weights / noise / tokens: eps at B=13, "
+                   "t=999, lambda=3; PSNR of the decoded images of a 2-level x 50-step progression (product decoder, and the "
+                   "oracle decoder on the product latents)"}
 
 
 # --------------------------------------------------------------------------------------------------- B200 arm
@@ -293,6 +356,62 @@ def run_b200(args) -> None:
         ln_s = e0.elapsed_time(e1) / 1e3 / reps
         ln_bytes = qx[0].numel() * 2 * 4
 
+        extras = {}
+        if not args.no_extras:
+            from progressive_stable_diffusion_b200.evaluation_pipeline import generate_all
+            # ---- strong scaling of config 2: 8 patients x 13 levels = 104 units IN TOTAL, split over the ranks ----
+            sp = 8 // world if 8 % world == 0 else 0                 # patients per rank
+            if sp == patients:
+                extras["strong"] = {"units_total": 8 * LEVELS, "units_per_gpu": batch, "value": batch * world * args.steps / seconds,
+                                    "unit": "img/s", "ms_per_step": seconds / args.steps * 1e3, "note": "identical to the headline run"}
+            elif 0 < sp < patients:
+                s_tok, s_src = d_tokens[:sp * LEVELS], d_source[:sp * LEVELS]
+                s_tgt, s_noise = d_target[:sp * LEVELS], d_noise[:sp * LEVELS]
+
+                def step_strong():
+                    lat = _sample(module, s_tgt, s_src, s_tok, s_noise, DDIM_STEPS, dev, 0.0, 1.0, None, STEER, 1.0, False, True)
+                    return _latents_to_images(module, lat)
+                for _ in range(3):
+                    step_strong()
+                sec = timed(step_strong, args.steps)
+                extras["strong"] = {"units_total": 8 * LEVELS, "units_per_gpu": sp * LEVELS, "value": 8 * LEVELS * args.steps / sec,
+                                    "unit": "img/s", "ms_per_step": sec / args.steps * 1e3,
+                                    "note": "fixed total work (8 patients x 13 levels) over all ranks; efficiency = value / (N=1 value) / N"}
+            # ---- config 4: one guidance scale of the evaluation sweep (50 samples x 4 classes), 50 steps, jobs sharded ----
+            n_jobs = 200
+            jobs = sorted((i % 16, float(i % 4), float(i // 50)) for i in range(n_jobs))       # (token set, source MES, target MES)
+            g4 = torch.Generator().manual_seed(4)
+            tok16 = torch.randn(16, 16, 768, generator=g4).to(dev)
+            bs4 = -(-n_jobs // world)
+            bs4 = min(bs4, 100)
+
+            def step_cfg4():
+                return generate_all(module, jobs, tok16, dev, batch_size=bs4, sampling_steps=DDIM_STEPS, steer_scale=STEER,
+                                    rank=rank, world_size=world)
+            step_cfg4()
+            sec = timed(step_cfg4, 1)
+            extras["config4"] = {"workload": "evaluation sweep, ONE of the 5 scales: 50 samples x 4 MES classes = 200 jobs x 50 DDIM steps "
+                                             "through generate_all (decode + copy to host included), jobs sharded over the ranks",
+                                 "jobs": n_jobs, "batch_per_rank": bs4, "value": n_jobs / sec, "unit": "img/s", "seconds": sec,
+                                 "full_sweep_estimate_s": 5 * sec}
+            # ---- config 5: 512x512 (64x64 latents) progression, 16 units in total ----
+            if 16 % world == 0:
+                u5 = 16 // world
+                t5 = torch.linspace(0.0, 3.0, 16, device=dev)[rank * u5:(rank + 1) * u5].contiguous()
+                s5 = torch.zeros(u5, device=dev)
+                k5 = d_tokens[:1].expand(u5, -1, -1).contiguous()
+                n5 = torch.randn(1, 4, 64, 64, generator=g4).to(dev).expand(u5, -1, -1, -1).contiguous()
+
+                def step_cfg5():
+                    lat = _sample(module, t5, s5, k5, n5, DDIM_STEPS, dev, 0.0, 1.0, None, STEER, 1.0, False, True)
+                    return _latents_to_images(module, lat)
+                step_cfg5()
+                step_cfg5()
+                sec = timed(step_cfg5, 2)
+                extras["config5"] = {"workload": "512x512 (64x64x4 latents) progression stress: 16 units x 50 DDIM steps, lambda=3, VAE decode "
+                                                 "included; self-attention at N=4096 / 1024 / 256", "units_total": 16, "units_per_gpu": u5,
+                                     "value": 16 * 2 / sec, "unit": "img/s", "ms_per_step": sec / 2 * 1e3}
+
         if args.profile_step:      # one eager denoising step between cudaProfilerStart/Stop (ncu --profile-from-start off)
             eng.state.zero_()
             eng._step()
@@ -319,16 +438,16 @@ def run_b200(args) -> None:
     unet_step()
     t_unet, t_dec = unet_step(), decode()
     cpu_progression = DDIM_STEPS * t_unet + t_dec
+    if not args.no_extras:
+        extras["parity"] = parity_block(dev, cdt)
     tflops = batch * world * args.steps * DDIM_STEPS * UNET_GFLOP_PER_SAMPLE_STEP / 1e3 / seconds
     _emit({
         "metric": "progression img/s (13 MES x 50 DDIM steps)", "value": value, "unit": "img/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": seconds / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "13 MES levels x 50 DDIM steps, lambda=3, 256x256, SD-1.x-shaped random-init weights, "
-                               "CFG off (routing gates), eta=0, VAE decode included",
-                   "patients_per_gpu": patients, "levels": LEVELS, "ddim_steps": DDIM_STEPS, "images_per_step_per_gpu": batch,
+        "config": {"workload": WORKLOAD, "patients_per_gpu": patients, "levels": LEVELS, "ddim_steps": DDIM_STEPS, "images_per_step_per_gpu": batch,
                    "parallelism": f"independent (patient x level) units, {world} rank(s), no data-path collective",
-                   "l2": "inputs larger than L2: 1.8 GB of bf16 weights stream through the 126 MB L2 on every UNet pass"},
+                   "l2": "inputs larger than L2: 1.8 GB of 16-bit weights stream through the 126 MB L2 on every UNet pass"},
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(host_pixels.numel() * 4 + host_source.numel() * 4 + host_noise.numel() * 4),
                 "path": "sample_progressions(host pixels (P,3,224,224) -> CLIP ViT-L/14 + resampler once per patient -> purifier/AOE -> "
                         "50 graph-replayed steps -> VAE decode) -> pinned host images",
@@ -341,8 +460,9 @@ def run_b200(args) -> None:
                      "achieved": attn_flop / attn_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": attn_flop / attn_s / 1e12 / pk["bf16_tflops"], "traffic": ncu_traffic("self_attn"),
                      "peak_source": pk["source"], "us_per_launch": attn_s * 1e6,
-                     "limiter": "MUFU.EX2 (16/clk/SM): 160 flop per exponential at d=40 caps the kernel at 744 TFLOP/s = 45 % "
-                                "of the tensor peak (profiles/r01_attn_poly_exp.txt)"},
+                     "limiter": "MUFU.EX2 (16/clk/SM = one warp instruction per 8 clk per scheduler): 160 flop per exponential at d=40 "
+                                "caps the kernel at 744 TFLOP/s = 45 % of the tensor peak; the kernel runs at 9.5 clk per exponential "
+                                "(profiles/r02_attn_microbench.txt)"},
         "roofline_groupnorm": {"kernel": "groupnorm+silu NHWC 320ch 32x32 at the bench batch", "bound": "hbm",
                                "achieved": gn_bytes / gn_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": gn_bytes / gn_s / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("groupnorm"),
@@ -357,6 +477,7 @@ def run_b200(args) -> None:
         "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
                                    f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},
+        **extras,
     })
 
 
@@ -367,8 +488,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--patients", type=int, default=8, help="patient progressions per GPU per step (13 images each)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
-                    help="16-bit operand type of the kernels (bf16 = the configuration BASELINE.json names; fp16 = same rate, 3 more mantissa bits)")
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="16-bit operand type of the kernels.  fp16 (default; the reference's own mixed-precision dtype, "
+                         "evaluation_pipeline.py:943) passes every north-star gate; bf16 has the same rate and bytes but lands at "
+                         "26-30 dB PSNR after 50 steps on random-init weights (profiles/r01_precision_experiment.txt)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity / strong / config4 / config5 legs")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the timed region run ONE eager denoising step inside cudaProfilerStart/Stop (for the ncu launch list)")
     args = ap.parse_args()

@@ -184,8 +184,7 @@ int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, cons
  * q, k, v: 16-bit (`dtype`: DADD_BF16 | DADD_F16) [B][N][*] with row strides (elements); head h at column h*d (so the
  * three can alias one fused [B][N][3C] projection output); o: same dtype and convention.  d % 8 == 0, d <= 160.
  * impl: 0 = shape dispatch (N >= 128 -> tcgen05/TMEM/TMA flash kernel, else warp-level mma.sync kernel),
- *       1 = force mma.sync, 2 = force tcgen05 (N >= 128 required; d <= 128 runs the persistent two-query-tile kernel,
- *       larger d the one-tile kernel), 3 = force the one-tile tcgen05 kernel.
+ *       1 = force mma.sync, 2 = force tcgen05 (N >= 128 required).
  */
 int dadd_self_attn_fwd(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride,
                        int64_t v_stride, void* o, int64_t o_stride, int B, int H, int N, int d, float scale,

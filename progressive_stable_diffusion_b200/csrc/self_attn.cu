@@ -1,8 +1,7 @@
 // K1 entry point: validation + shape dispatch of the self-attention core.
 // Reference op: F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0
 // (src/models/attention_processor_routing_gates.py:284-286).
-//   N >= 128, d <= 128  -> tcgen05 / TMEM / TMA flash kernel, two ping-ponged query tiles per persistent CTA (self_attn_tc2.cu)
-//   N >= 128, d  > 128  -> tcgen05 / TMEM / TMA flash kernel, one query tile per CTA (self_attn_tc.cu)
+//   N >= 128            -> tcgen05 / TMEM / TMA flash kernel, two query tiles per persistent CTA (self_attn_tc.cu)
 //   N <  128 (64, 16)   -> warp-level mma.sync kernel (self_attn_mma.cu): one KV tile, latency-bound sites
 #include <cstdlib>
 
@@ -14,19 +13,15 @@ int self_attn_mma(const void* q, const void* k, const void* v, int64_t qs, int64
 int self_attn_tc(const void* q, const void* k, const void* v, int64_t qs, int64_t ks, int64_t vs, void* o, int64_t os,
                  int B, int H, int N, int d, float scale, int dtype, cudaStream_t s);
 bool self_attn_tc_supported(int N, int d);
-int self_attn_tc2(const void* q, const void* k, const void* v, int64_t qs, int64_t ks, int64_t vs, void* o, int64_t os,
-                  int B, int H, int N, int d, float scale, int dtype, cudaStream_t s);
-bool self_attn_tc2_supported(int N, int d);
 }  // namespace daddk
 
 using namespace daddk;
 
-// DADD_SELF_ATTN=mma|tc|tc1 forces one implementation (tests and A/B timing); default is the shape dispatch above.
+// DADD_SELF_ATTN=mma|tc forces one implementation (tests and A/B timing); default is the shape dispatch above.
 static int forced_impl() {
     static const int v = [] {
         const char* e = getenv("DADD_SELF_ATTN");
         if (!e) return 0;
-        if (e[0] == 't' && e[1] == 'c' && e[2] == '1') return 3;
         return e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0);
     }();
     return v;
@@ -37,7 +32,7 @@ extern "C" int dadd_self_attn_fwd(const void* q, const void* k, const void* v, i
                                   int dtype, int impl, void* stream) {
     DADD_REQUIRE(q && k && v && o, "dadd_self_attn_fwd");
     DADD_REQUIRE(dtype16_ok(dtype), "dadd_self_attn_fwd");
-    DADD_REQUIRE(impl >= 0 && impl <= 3, "dadd_self_attn_fwd");
+    DADD_REQUIRE(impl >= 0 && impl <= 2, "dadd_self_attn_fwd");
     DADD_REQUIRE(B >= 0 && H > 0 && N >= 0 && B <= 65535 && H <= 65535, "dadd_self_attn_fwd");
     DADD_REQUIRE(d > 0 && d % 8 == 0 && d <= 160, "dadd_self_attn_fwd");
     DADD_REQUIRE(q_stride % 8 == 0 && k_stride % 8 == 0 && v_stride % 8 == 0 && o_stride % 8 == 0, "dadd_self_attn_fwd");
@@ -47,9 +42,7 @@ extern "C" int dadd_self_attn_fwd(const void* q, const void* k, const void* v, i
     if (B == 0 || N == 0) return 0;
     if (impl == 0) impl = forced_impl();
     if (impl == 0) impl = (N >= 128 && self_attn_tc_supported(N, d)) ? 2 : 1;
-    if (impl == 2 && self_attn_tc2_supported(N, d))
-        return self_attn_tc2(q, k, v, q_stride, k_stride, v_stride, o, o_stride, B, H, N, d, scale, dtype, (cudaStream_t)stream);
-    if (impl == 2 || impl == 3) {
+    if (impl == 2) {
         DADD_REQUIRE(self_attn_tc_supported(N, d), "dadd_self_attn_fwd(tcgen05)");
         return self_attn_tc(q, k, v, q_stride, k_stride, v_stride, o, o_stride, B, H, N, d, scale, dtype, (cudaStream_t)stream);
     }

@@ -317,7 +317,7 @@ def cross_attention(q: torch.Tensor, k_cat: torch.Tensor, v_cat: torch.Tensor, g
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
                    impl: str = "auto") -> torch.Tensor:
     """softmax(q k^T scale) v per head; q,k,v (B,N,H*d) bf16/fp16, possibly strided views of one fused QKV buffer.
-    ``impl``: "auto" (N >= 128 -> tcgen05 kernel, else mma.sync kernel), "mma", "tc" or "tc1" (one-query-tile tcgen05)."""
+    ``impl``: "auto" (N >= 128 -> tcgen05 kernel, else mma.sync kernel), "mma" or "tc"."""
     _cuda(q, k, v)
     b, n, c = q.shape
     d = c // heads
@@ -326,7 +326,7 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
     _lib.check(_lib.load().dadd_self_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _rows(q), _rows(k), _rows(v),
                                               o.data_ptr(), c, b, heads, n, d,
                                               float(d ** -0.5 if scale is None else scale), _dt(q),
-                                              {"auto": 0, "mma": 1, "tc": 2, "tc1": 3}[impl], _stream()),
+                                              {"auto": 0, "mma": 1, "tc": 2}[impl], _stream()),
                "dadd_self_attn_fwd")
     return o
 
