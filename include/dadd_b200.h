@@ -30,7 +30,7 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change).  The host binding refuses a library whose
  * dadd_abi_version() differs from the DADD_ABI_VERSION it was written against. */
-#define DADD_ABI_VERSION 9
+#define DADD_ABI_VERSION 10
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -212,6 +212,41 @@ int dadd_aoe_interp_fwd(const float* base, const float* deltas, const float* lab
 /* Latents -> displayable images tail of _latents_to_images (src/pipelines/inference/inference_pipeline_ip.py:483-485):
  * y = clamp((clamp(x, -1, 1) + 1) / 2, 0, 1); x `dtype` (decoder output), y fp32. */
 int dadd_image_post_fwd(const void* x, float* y, int64_t n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step: what Lightning autograd + torch.optim run for the reference at
+ * src/models/diffusion_module_ip.py:392-462 (training_step: MSE x Min-SNR weight), :500-536 (AdamW groups) and
+ * src/pipelines/training/training_pipeline_ip.py:103-123 (gradient_clip_val, precision "16-mixed", DDP).
+ * All reductions are two-stage and atomics-free (bit-reproducible).
+ *
+ * LayerNorm backward: x, dy, dx [rows][C] 16-bit; gamma [C]; dgamma / dbeta are the two rows of ONE fp32 (2, C) buffer
+ * (dbeta == dgamma + C); workspace: dadd_layernorm_bwd_workspace_bytes(C).  Statistics are recomputed from x. */
+int64_t dadd_layernorm_bwd_workspace_bytes(int C);
+int dadd_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                       float* workspace, int64_t rows, int C, float eps, int dtype, void* stream);
+/* GEGLU backward: proj [M][2 inner] = [value | gate], dy [M][inner] -> dproj [M][2 inner]; exact (erf) GELU. */
+int dadd_geglu_bwd(const void* proj, const void* dy, void* dproj, int64_t M, int inner, int dtype, void* stream);
+/* GroupNorm (+ chan_add[b][c]) (+ SiLU) backward, NHWC: x, dy, dx [B][HW][C] 16-bit; gamma, beta, dgamma, dbeta [C] fp32;
+ * chan_add / dchan_add [B][C] fp32 or NULL (dchan_add needs chan_add).  Statistics are recomputed from x. */
+int64_t dadd_groupnorm_bwd_workspace_bytes(int B, int C, int HW, int G);
+int dadd_groupnorm_bwd(const void* x, const float* chan_add, const void* dy, const float* gamma, const float* beta,
+                       void* dx, float* dgamma, float* dbeta, float* dchan_add, float* workspace, int B, int HW, int C,
+                       int G, float eps, int apply_silu, int dtype, void* stream);
+/* loss[0] = mean_b weight[b] * mean_e (pred - target)^2 (diffusion_module_ip.py:449-452); grad (optional) = upstream *
+ * dloss/dpred.  pred, target, grad [B][E] fp32; workspace: dadd_minsnr_mse_workspace_bytes(B). */
+int64_t dadd_minsnr_mse_workspace_bytes(int B);
+int dadd_minsnr_mse(const float* pred, const float* target, const float* weight, float* loss, float* grad,
+                    float* workspace, int B, int64_t E, float upstream, void* stream);
+/* Gradient-norm clipping and AdamW over flat fp32 buckets, no host synchronisation:
+ * dadd_sumsq writes n_partials partial sums of g^2; dadd_clip_coef turns ALL partials of a step into
+ * coef_and_norm[0] = grad_scale * min(1, max_norm / (norm + 1e-6)) (max_norm <= 0: no clipping) and [1] = norm =
+ * grad_scale * sqrt(sum) (torch.nn.utils.clip_grad_norm_; grad_scale = 1 / world size when the buckets hold SUMS);
+ * dadd_adamw_step applies torch.optim.AdamW's update with g scaled by coef[0] (coef may be NULL).  A non-finite norm (fp16
+ * overflow under a loss scale; fold 1 / loss_scale into grad_scale) makes coef[0] NaN and the AdamW launches no-ops. */
+int dadd_sumsq(const float* g, int64_t n, float* partials, int n_partials, void* stream);
+int dadd_clip_coef(const float* partials, int n, float max_norm, float grad_scale, float* coef_and_norm, void* stream);
+int dadd_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float bias_corr1, float bias_corr2, const float* coef, void* stream);
 
 #ifdef __cplusplus
 }

@@ -159,6 +159,33 @@ def vae_decode(w: W, z: torch.Tensor) -> torch.Tensor:
     return _conv(h, w, "decoder.conv_out")
 
 
+def _vae_mid_attention(w: W, a: str, h: torch.Tensor) -> torch.Tensor:
+    b, c, hh, ww = h.shape
+    x = F.group_norm(h.view(b, c, hh * ww), 32, w[a + ".group_norm.weight"], w[a + ".group_norm.bias"], 1e-6).transpose(1, 2)
+    q = F.linear(x, w[a + ".to_q.weight"], w[a + ".to_q.bias"])
+    k = F.linear(x, w[a + ".to_k.weight"], w[a + ".to_k.bias"])
+    v = F.linear(x, w[a + ".to_v.weight"], w[a + ".to_v.bias"])
+    o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+    o = F.linear(o, w[a + ".to_out.0.weight"], w[a + ".to_out.0.bias"])
+    return h + o.transpose(1, 2).reshape(b, c, hh, ww)
+
+
+def vae_encode_moments(w: W, images: torch.Tensor) -> torch.Tensor:
+    """``AutoencoderKL.encode(x)`` up to the posterior's moments [mean | logvar] (B, 8, H/8, W/8): Encoder -> quant_conv
+    (diffusers graph; called at src/models/diffusion_module_ip.py:419).  Downsample2D(padding=0) pads right / bottom by one."""
+    h = _conv(images, w, "encoder.conv_in")
+    for i in range(4):
+        for j in range(2):
+            h = resnet_block(w, f"encoder.down_blocks.{i}.resnets.{j}", h, None, eps=1e-6)
+        if i < 3:
+            h = _conv(F.pad(h, (0, 1, 0, 1)), w, f"encoder.down_blocks.{i}.downsamplers.0.conv", stride=2, padding=0)
+    h = resnet_block(w, "encoder.mid_block.resnets.0", h, None, eps=1e-6)
+    h = _vae_mid_attention(w, "encoder.mid_block.attentions.0", h)
+    h = resnet_block(w, "encoder.mid_block.resnets.1", h, None, eps=1e-6)
+    h = _conv(_gn(h, w, "encoder.conv_norm_out", 1e-6, True), w, "encoder.conv_out")
+    return _conv(h, w, "quant_conv", padding=0)
+
+
 def latents_to_images(vae_w: W, latents: torch.Tensor, latent_scale: float = 0.18215) -> torch.Tensor:
     """``_latents_to_images`` (inference_pipeline_ip.py:473-486)."""
     img = vae_decode(vae_w, latents / latent_scale).clamp(-1.0, 1.0)

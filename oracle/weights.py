@@ -191,6 +191,31 @@ def make_vae_decoder_state(seed: int = 1, gain: float = 1.0, affine_jitter: floa
     return {prefix + k: v for k, v in it.sd.items()}
 
 
+def make_vae_encoder_state(seed: int = 7, gain: float = 1.0, affine_jitter: float = 0.1, prefix: str = "") -> State:
+    """SD AutoencoderKL encoder half (+ quant_conv): the frozen first step of the reference's training_step
+    (diffusion_module_ip.py:419-420 ``vae.encode(images).latent_dist.sample()``)."""
+    it = _Init(seed, gain, affine_jitter)
+    it.conv("encoder.conv_in", 3, 128, 3)
+    chans = (128, 256, 512, 512)
+    cin = 128
+    for i, cout in enumerate(chans):
+        for j in range(2):
+            _resnet(it, f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, None)
+        if i < 3:
+            it.conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+        cin = cout
+    _resnet(it, "encoder.mid_block.resnets.0", 512, 512, None)
+    a = "encoder.mid_block.attentions.0"
+    it.norm(a + ".group_norm", 512)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        it.linear(f"{a}.{n}", 512, 512)
+    _resnet(it, "encoder.mid_block.resnets.1", 512, 512, None)
+    it.norm("encoder.conv_norm_out", 512)
+    it.conv("encoder.conv_out", 512, 8, 3)
+    it.conv("quant_conv", 8, 8, 1)
+    return {prefix + k: v for k, v in it.sd.items()}
+
+
 def make_purifier_state(seed: int = 2, dim: int = 768, ff_mult: int = 2, affine_jitter: float = 0.1,
                         prefix: str = "") -> State:
     """Keys of ``FeaturePurifier`` (feature_purifier.py:46-62): nn.MultiheadAttention packs q/k/v."""

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DADD_B200_LIB") or os.path.join(HERE, "libdadd_b200.s
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
-ABI_VERSION = 9          # == DADD_ABI_VERSION of include/dadd_b200.h that SIGNATURES below was written against
+ABI_VERSION = 10         # == DADD_ABI_VERSION of include/dadd_b200.h that SIGNATURES below was written against
 
 # name -> argtypes; mirrors include/dadd_b200.h one to one (tests/test_abi.py checks header <-> table <-> .so)
 SIGNATURES = {
@@ -40,6 +40,17 @@ SIGNATURES = {
     "dadd_purifier_gate_ln_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "dadd_aoe_interp_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "dadd_image_post_fwd": [_P, _P, _L, _I, _P],
+    # training step
+    "dadd_layernorm_bwd_workspace_bytes": [_I],
+    "dadd_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
+    "dadd_geglu_bwd": [_P, _P, _P, _L, _I, _I, _P],
+    "dadd_groupnorm_bwd_workspace_bytes": [_I, _I, _I, _I],
+    "dadd_groupnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P],
+    "dadd_minsnr_mse_workspace_bytes": [_I],
+    "dadd_minsnr_mse": [_P, _P, _P, _P, _P, _P, _I, _L, _F, _P],
+    "dadd_sumsq": [_P, _L, _P, _I, _P],
+    "dadd_clip_coef": [_P, _I, _F, _F, _P, _P],
+    "dadd_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P, _P],
 }
 
 _lib = None

@@ -107,7 +107,7 @@ def default_config(**model_overrides) -> AttrDict:
 
 
 class DiffusionModuleWithIP(nn.Module):
-    def __init__(self, cfg: Any, build_vae: bool = True, build_image_encoder: bool = False) -> None:
+    def __init__(self, cfg: Any, build_vae: bool = True, build_image_encoder: bool = False, build_vae_encoder: bool = False) -> None:
         super().__init__()
         self.cfg = cfg
         m, d = cfg.model, cfg.diffusion
@@ -130,7 +130,7 @@ class DiffusionModuleWithIP(nn.Module):
             gate_init_anatomy=tuple(getattr(m, "gate_init_anatomy", [0.5, 0.5])),
             gate_init_disease=tuple(getattr(m, "gate_init_disease", [0.5, 0.5])),
         )
-        self.vae = SDVAE(getattr(m, "pretrained_vae_path", None)) if build_vae else None
+        self.vae = SDVAE(getattr(m, "pretrained_vae_path", None), build_encoder=build_vae_encoder) if build_vae else None
         self.image_encoder = None        # frozen CLIP tower + trainable projection (reference :130-149)
         self.image_projection = None
         if build_image_encoder:

@@ -373,3 +373,98 @@ def image_post(x: torch.Tensor) -> torch.Tensor:
     assert y.stride() == x.stride()
     _lib.check(_lib.load().dadd_image_post_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _dt(x), _stream()), "dadd_image_post_fwd")
     return y
+
+
+# --------------------------------------------------------------------------------------------- training step (backward, loss, optimizer)
+def layer_norm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float):
+    """Backward of ``layer_norm``: (dx like x, dgamma (C,) fp32, dbeta (C,) fp32); statistics recomputed from ``x``."""
+    _cuda(x, dy, gamma)
+    c = x.shape[-1]
+    assert x.is_contiguous() and dy.is_contiguous() and x.shape == dy.shape and x.dtype == dy.dtype
+    assert gamma.dtype == torch.float32 and gamma.numel() == c
+    rows = x.numel() // c
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+    ws = torch.empty(max(int(lib.dadd_layernorm_bwd_workspace_bytes(c)), 8), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.dadd_layernorm_bwd(x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), dx.data_ptr(), dgb[0].data_ptr(),
+                                      dgb[1].data_ptr(), ws.data_ptr(), rows, c, eps, _dt(x), _stream()), "dadd_layernorm_bwd")
+    return dx, dgb[0], dgb[1]
+
+
+def geglu_bwd(proj: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """Backward of ``geglu``: ``proj`` (..., 2I) = [value | gate], ``dy`` (..., I) -> dproj like proj."""
+    _cuda(proj, dy)
+    inner = dy.shape[-1]
+    assert proj.is_contiguous() and dy.is_contiguous() and proj.shape[-1] == 2 * inner and proj.dtype == dy.dtype
+    dproj = torch.empty_like(proj)
+    _lib.check(_lib.load().dadd_geglu_bwd(proj.data_ptr(), dy.data_ptr(), dproj.data_ptr(), dy.numel() // inner, inner, _dt(proj),
+                                          _stream()), "dadd_geglu_bwd")
+    return dproj
+
+
+def group_norm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, num_groups: int, eps: float,
+                   silu: bool, chan_add: Optional[torch.Tensor] = None, need_dchan_add: bool = False):
+    """Backward of ``group_norm`` on channels_last tensors: (dx, dgamma, dbeta, dchan_add or None)."""
+    _cuda(x, dy, gamma, beta, chan_add)
+    assert x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and dy.shape == x.shape and dy.dtype == x.dtype
+    if not dy.is_contiguous(memory_format=torch.channels_last):
+        dy = dy.contiguous(memory_format=torch.channels_last)
+    b, c, h, w = x.shape
+    if chan_add is not None:
+        assert chan_add.dtype == torch.float32 and chan_add.shape == (b, c)
+        chan_add = chan_add.contiguous()
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    dadd = torch.empty(b, c, dtype=torch.float32, device=x.device) if (need_dchan_add and chan_add is not None) else None
+    ws = torch.empty(max(int(lib.dadd_groupnorm_bwd_workspace_bytes(b, c, h * w, num_groups)), 8), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.dadd_groupnorm_bwd(x.data_ptr(), _ptr(chan_add), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dx.data_ptr(),
+                                      dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dadd), ws.data_ptr(), b, h * w, c, num_groups, eps,
+                                      int(silu), _dt(x), _stream()), "dadd_groupnorm_bwd")
+    return dx, dgamma, dbeta, dadd
+
+
+def minsnr_mse(pred: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, need_grad: bool = True, upstream: float = 1.0):
+    """loss = mean_b weight[b] * mean(pred[b] - target[b])^2 and (optionally) dloss/dpred * upstream, one pass."""
+    _cuda(pred, target, weight)
+    assert pred.dtype == torch.float32 and target.dtype == torch.float32 and weight.dtype == torch.float32
+    assert pred.is_contiguous() and target.is_contiguous() and pred.shape == target.shape and weight.numel() == pred.shape[0]
+    b = pred.shape[0]
+    e = pred.numel() // b
+    lib = _lib.load()
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if need_grad else None
+    ws = torch.empty(int(lib.dadd_minsnr_mse_workspace_bytes(b)), dtype=torch.uint8, device=pred.device)
+    _lib.check(lib.dadd_minsnr_mse(pred.data_ptr(), target.data_ptr(), weight.data_ptr(), loss.data_ptr(), _ptr(grad), ws.data_ptr(),
+                                   b, e, upstream, _stream()), "dadd_minsnr_mse")
+    return loss[0], grad
+
+
+SUMSQ_PARTIALS = 296      # partial sums per flat buffer (2 x 148 SMs)
+
+
+def sumsq_(g: torch.Tensor, partials: torch.Tensor) -> None:
+    """partials[:] = SUMSQ_PARTIALS partial sums of g^2 (flat fp32)."""
+    _cuda(g, partials)
+    assert g.dtype == torch.float32 and g.is_contiguous() and partials.dtype == torch.float32 and partials.is_contiguous()
+    _lib.check(_lib.load().dadd_sumsq(g.data_ptr(), g.numel(), partials.data_ptr(), partials.numel(), _stream()), "dadd_sumsq")
+
+
+def clip_coef_(partials: torch.Tensor, max_norm: float, grad_scale: float, coef_and_norm: torch.Tensor) -> None:
+    _cuda(partials, coef_and_norm)
+    assert partials.dtype == torch.float32 and partials.is_contiguous() and coef_and_norm.numel() >= 2
+    _lib.check(_lib.load().dadd_clip_coef(partials.data_ptr(), partials.numel(), max_norm, grad_scale, coef_and_norm.data_ptr(),
+                                          _stream()), "dadd_clip_coef")
+
+
+def adamw_step_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
+                eps: float, weight_decay: float, step: int, coef: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.AdamW's update on flat fp32 buffers, in place; ``g`` is scaled by ``coef[0]`` (device scalar) on the fly."""
+    _cuda(p, g, m, v, coef)
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    _lib.check(_lib.load().dadd_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                                           weight_decay, 1.0 - beta1 ** step, 1.0 - beta2 ** step, _ptr(coef), _stream()),
+               "dadd_adamw_step")
