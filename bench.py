@@ -17,7 +17,9 @@ After the headline the same run adds (each a separate object of the JSON line):
 ``strong``   BASELINE config 2 read as STRONG scaling: 8 patients x 13 levels = 104 units in total, split over the ranks;
 ``config4``  one guidance scale of the evaluation sweep (50 samples x 4 MES classes = 200 jobs, 50 steps) through
              ``evaluation_pipeline.generate_all``, jobs sharded over the ranks;
-``config5``  the 512x512 stress progression, batch 16 in total split over the ranks.
+``config5``  the 512x512 stress progression, batch 16 in total split over the ranks;
+``config3``  the training step (batch 8 per GPU, bf16, 256x256: frozen VAE encode + CLIP, conditioning, UNet forward /
+             backward, bucketed gradient all-reduce over NCCL, clip + AdamW), with the all-reduce's exposed share.
 """
 
 from __future__ import annotations
@@ -245,7 +247,7 @@ def run_b200(args) -> None:
     P.set_compute_dtype(cdt)
 
     torch.manual_seed(0)                                          # random-init SD-1.x-shaped weights (PyTorch default inits)
-    module = P.DiffusionModuleWithIP(P.default_config(), build_image_encoder=True)     # + random-init CLIP ViT-L/14 + resampler
+    module = P.DiffusionModuleWithIP(P.default_config(), build_image_encoder=True, build_vae_encoder=True)     # + random-init CLIP ViT-L/14 + resampler, VAE encoder (training leg)
     module.to(dev).eval()
 
     g = torch.Generator().manual_seed(100 + rank)
@@ -416,6 +418,7 @@ def run_b200(args) -> None:
                                                  "included; self-attention at N=4096 / 1024 / 256", "units_total": 16, "units_per_gpu": u5,
                                      "value": 16 * 2 / sec, "unit": "img/s", "ms_per_step": sec / 2 * 1e3}
 
+    with torch.no_grad():
         if args.profile_step:      # one eager denoising step between cudaProfilerStart/Stop (ncu --profile-from-start off)
             eng.state.zero_()
             eng._step()
@@ -425,6 +428,36 @@ def run_b200(args) -> None:
             eng._step()
             torch.cuda.synchronize(dev)
             torch.cuda.profiler.stop()
+
+    if not args.no_extras:
+        # ---- config 3: training step, batch 8 per GPU, bf16, DDP gradient all-reduce (LAST: it updates the weights) ----
+        from progressive_stable_diffusion_b200 import training as T
+        tb = 8
+        gt = torch.Generator(device=dev).manual_seed(300 + rank)
+        t_images = torch.rand(tb, 3, 256, 256, device=dev, generator=gt) * 2 - 1
+        t_struct = torch.randn(tb, 3, 224, 224, device=dev, generator=gt)
+        t_labels = torch.randint(0, 4, (tb,), device=dev, generator=gt).float()
+        trainer = T.DataParallelTrainer(module, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0)
+        step_train = lambda: trainer.step(lambda: T.training_step(module, (t_images, t_labels, t_struct), generator=gt,
+                                                                   compute_dtype=torch.bfloat16))
+        for _ in range(2):
+            step_train()
+        _lib.reset_launch_count()
+        sec = timed(step_train, 3)
+        train_launches = _lib.launch_count() // 3
+        extras["config3"] = {"workload": "training step, batch 8 per GPU, bf16 compute / fp32 master weights, 256x256: VAE encode + CLIP "
+                                         "(frozen), AOE / purifier / resampler, UNet forward + backward, Min-SNR loss, bucketed all-reduce, "
+                                         "clip 1.0, AdamW (4 groups)", "batch_per_gpu": tb, "value": tb * world * 3 / sec, "unit": "img/s",
+                             "ms_per_step": sec / 3 * 1e3, "dadd_launches_per_step": int(train_launches),
+                             "grad_buckets": len(trainer.buckets), "grad_bytes": int(sum(bk.numel for bk in trainer.buckets) * 4)}
+        if world > 1:           # exposed share of the gradient all-reduce: the same step with the collective switched off
+            trainer.world = 1
+            step_train()
+            sec_off = timed(step_train, 3)
+            trainer.world = world
+            extras["config3"]["ms_per_step_without_allreduce"] = sec_off / 3 * 1e3
+            extras["config3"]["allreduce_exposed_share"] = max(0.0, 1.0 - sec_off / sec)
+        del trainer
 
     images_total = batch * world * args.steps
     value = images_total / seconds
