@@ -510,7 +510,7 @@ def run_b200(args) -> None:
                                 "us_per_launch": xa_s * 1e6},
         "roofline_add_layernorm": {"kernel": "residual add + LayerNorm (N=1024, C=320) at the bench batch", "bound": "hbm",
                                    "achieved": ln_bytes / ln_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                   "frac": ln_bytes / ln_s / 1e9 / pk["hbm_gbs"], "traffic": None, "us_per_launch": ln_s * 1e6},
+                                   "frac": ln_bytes / ln_s / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("add_layernorm"), "us_per_launch": ln_s * 1e6},
         "cpu_baseline": {"value": LEVELS / cpu_progression, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"1 UNet denoising step at B=13 ({t_unet:.2f} s) + 1 VAE decode at B=13 ({t_dec:.2f} s) through the "
                                    f"oracle port (fp32 eager); 13x50 progression extrapolated = {cpu_progression:.1f} s"},

@@ -232,6 +232,13 @@ int64_t dadd_groupnorm_bwd_workspace_bytes(int B, int C, int HW, int G);
 int dadd_groupnorm_bwd(const void* x, const float* chan_add, const void* dy, const float* gamma, const float* beta,
                        void* dx, float* dgamma, float* dbeta, float* dchan_add, float* workspace, int B, int HW, int C,
                        int G, float eps, int apply_silu, int dtype, void* stream);
+/* Backward of dadd_cross_attn_fwd's core (attention_processor_routing_gates.py:148-178) for the training step: q, dout, dq
+ * [B][N][*] 16-bit with row strides (head h at column h*d), k_cat / v_cat [B][H][L][d] 16-bit (L = n_seg * seg_len <= 48),
+ * gates [n_seg] fp32 (device); dk, dv [B][H][L][d] fp32.  workspace: dadd_cross_attn_bwd_workspace_bytes(...). */
+int64_t dadd_cross_attn_bwd_workspace_bytes(int B, int H, int N, int d, int L);
+int dadd_cross_attn_bwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, const float* gates,
+                        const void* dout, int64_t do_stride, void* dq, int64_t dq_stride, float* dk, float* dv,
+                        float* workspace, int B, int H, int N, int d, int L, int seg_len, float scale, int dtype, void* stream);
 /* loss[0] = mean_b weight[b] * mean_e (pred - target)^2 (diffusion_module_ip.py:449-452); grad (optional) = upstream *
  * dloss/dpred.  pred, target, grad [B][E] fp32; workspace: dadd_minsnr_mse_workspace_bytes(B). */
 int64_t dadd_minsnr_mse_workspace_bytes(int B);

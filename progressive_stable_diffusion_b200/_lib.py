@@ -46,6 +46,8 @@ SIGNATURES = {
     "dadd_geglu_bwd": [_P, _P, _P, _L, _I, _I, _P],
     "dadd_groupnorm_bwd_workspace_bytes": [_I, _I, _I, _I],
     "dadd_groupnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P],
+    "dadd_cross_attn_bwd_workspace_bytes": [_I, _I, _I, _I, _I],
+    "dadd_cross_attn_bwd": [_P, _L, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "dadd_minsnr_mse_workspace_bytes": [_I],
     "dadd_minsnr_mse": [_P, _P, _P, _P, _P, _P, _I, _L, _F, _P],
     "dadd_sumsq": [_P, _L, _P, _I, _P],

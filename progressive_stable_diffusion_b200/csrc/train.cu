@@ -611,3 +611,166 @@ extern "C" int dadd_adamw_step(float* p, const float* g, float* m, float* v, int
     adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, coef);
     return launched("dadd_adamw_step");
 }
+
+// ------------------------------------------------------------------------------------------------ cross-attention backward
+// Backward of the triple-pathway core (dadd_cross_attn_fwd; attention_processor_routing_gates.py:148-178): per (sample, head)
+//   o_i = sum_s g_s sum_{j in seg s} p_ij v_j,   p = per-segment softmax(q_i . k_j * scale)
+//   dp_ij = g_s (do_i . v_j),  ds_ij = p_ij (dp_ij - sum_{j' in seg} p_ij' dp_ij'),
+//   dq_i = scale sum_j ds_ij k_j,  dk_j = scale sum_i ds_ij q_i,  dv_j = sum_i g_s p_ij do_i.
+// L <= 48 condition tokens: 480 d flop per query row - 0.3 % of the training step - so this runs on the CUDA cores in fp32.
+// CTA = one (sample, head) x one slice of query rows, walking 32-row tiles: K, V and the tile of Q / dO sit in shared memory
+// (pitch d + 1), dK / dV accumulate in registers across the tiles (fixed order), the slices' partials are summed by a second
+// kernel: no atomics, bit-reproducible.
+namespace daddk {
+constexpr int XB_ROWS = 32, XB_THREADS = 256, XB_MAXOUT = 30;      // 48 * 160 / 256 outputs per thread at most
+
+template <typename T>
+__global__ void __launch_bounds__(XB_THREADS) cross_attn_bwd_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kc,
+                                                                    const T* __restrict__ vc, const float* __restrict__ gates,
+                                                                    const T* __restrict__ dout, int64_t do_stride, T* __restrict__ dq,
+                                                                    int64_t dq_stride, float* __restrict__ dk_part, float* __restrict__ dv_part,
+                                                                    int H, int N, int d, int L, int seg_len, float scale, int rows_per_split) {
+    extern __shared__ float xb_sm[];
+    const int dp = d + 1, lp = L + 1;
+    float* sK = xb_sm;                      // [L][dp]
+    float* sV = sK + L * dp;                // [L][dp]
+    float* sQ = sV + L * dp;                // [32][dp]
+    float* sD = sQ + XB_ROWS * dp;          // [32][dp]   dO tile
+    float* sS = sD + XB_ROWS * dp;          // [32][lp]   scores -> scale * dS
+    float* sP = sS + XB_ROWS * lp;          // [32][lp]   dP -> gate * P
+    const int tid = threadIdx.x, bh = blockIdx.x, b = bh / H, h = bh % H, split = blockIdx.y, splits = gridDim.y;
+    const int nseg = L / seg_len;
+    const int row0 = split * rows_per_split, row1 = min(N, row0 + rows_per_split);
+    const T* kb = kc + (size_t)bh * L * d;
+    const T* vb = vc + (size_t)bh * L * d;
+    for (int i = tid; i < L * d; i += XB_THREADS) {
+        sK[(i / d) * dp + i % d] = to_f(kb[i]);
+        sV[(i / d) * dp + i % d] = to_f(vb[i]);
+    }
+    float dka[XB_MAXOUT], dva[XB_MAXOUT];
+#pragma unroll
+    for (int i = 0; i < XB_MAXOUT; ++i) dka[i] = dva[i] = 0.0f;
+    for (int r0 = row0; r0 < row1; r0 += XB_ROWS) {
+        __syncthreads();                                            // previous tile fully consumed (and K / V loaded)
+        for (int i = tid; i < XB_ROWS * d; i += XB_THREADS) {
+            const int r = i / d, c = i % d, row = r0 + r;
+            const bool live = row < row1;
+            sQ[r * dp + c] = live ? to_f(q[((size_t)b * N + row) * q_stride + h * d + c]) : 0.0f;
+            sD[r * dp + c] = live ? to_f(dout[((size_t)b * N + row) * do_stride + h * d + c]) : 0.0f;
+        }
+        __syncthreads();
+        for (int i = tid; i < XB_ROWS * L; i += XB_THREADS) {
+            const int r = i / L, j = i % L;
+            float s = 0.0f, g = 0.0f;
+            for (int c = 0; c < d; ++c) {
+                s = fmaf(sQ[r * dp + c], sK[j * dp + c], s);
+                g = fmaf(sD[r * dp + c], sV[j * dp + c], g);
+            }
+            sS[r * lp + j] = s * scale;
+            sP[r * lp + j] = g * gates[j / seg_len];
+        }
+        __syncthreads();
+        for (int i = tid; i < XB_ROWS * nseg; i += XB_THREADS) {
+            const int r = i / nseg, sg = i % nseg;
+            float* s = sS + r * lp + sg * seg_len;
+            float* p = sP + r * lp + sg * seg_len;
+            const float gate = gates[sg];
+            float m = -INFINITY;
+            for (int j = 0; j < seg_len; ++j) m = fmaxf(m, s[j]);
+            float sum = 0.0f;
+            for (int j = 0; j < seg_len; ++j) { s[j] = __expf(s[j] - m); sum += s[j]; }
+            const float inv = 1.0f / sum;
+            float dot = 0.0f;
+            for (int j = 0; j < seg_len; ++j) { s[j] *= inv; dot = fmaf(s[j], p[j], dot); }
+            for (int j = 0; j < seg_len; ++j) {
+                const float pj = s[j];
+                s[j] = scale * pj * (p[j] - dot);                  // scale * dS
+                p[j] = gate * pj;                                   // gate * P
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < XB_ROWS * d; i += XB_THREADS) {
+            const int r = i / d, c = i % d, row = r0 + r;
+            if (row < row1) {
+                float a = 0.0f;
+                for (int j = 0; j < L; ++j) a = fmaf(sS[r * lp + j], sK[j * dp + c], a);
+                if constexpr (std::is_same_v<T, __nv_bfloat16>) dq[((size_t)b * N + row) * dq_stride + h * d + c] = __float2bfloat16(a);
+                else dq[((size_t)b * N + row) * dq_stride + h * d + c] = __float2half(a);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < XB_MAXOUT; ++i) {
+            const int o = tid + i * XB_THREADS;
+            if (o < L * d) {
+                const int j = o / d, c = o % d;
+                float a = dka[i], v = dva[i];
+#pragma unroll 8
+                for (int r = 0; r < XB_ROWS; ++r) {
+                    a = fmaf(sS[r * lp + j], sQ[r * dp + c], a);
+                    v = fmaf(sP[r * lp + j], sD[r * dp + c], v);
+                }
+                dka[i] = a;
+                dva[i] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < XB_MAXOUT; ++i) {
+        const int o = tid + i * XB_THREADS;
+        if (o < L * d) {
+            dk_part[((size_t)bh * splits + split) * L * d + o] = dka[i];
+            dv_part[((size_t)bh * splits + split) * L * d + o] = dva[i];
+        }
+    }
+}
+
+// out[bh][o] = sum_split part[bh][split][o], both tensors in one launch (blockIdx.y selects dK / dV)
+__global__ void cross_attn_bwd_reduce_kernel(const float* __restrict__ dk_part, const float* __restrict__ dv_part, float* __restrict__ dk,
+                                             float* __restrict__ dv, int64_t total, int per, int splits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float* part = blockIdx.y ? dv_part : dk_part;
+    const int64_t bh = i / per, o = i % per;
+    float a = 0.0f;
+    for (int s = 0; s < splits; ++s) a += part[(bh * splits + s) * per + o];
+    (blockIdx.y ? dv : dk)[i] = a;
+}
+}  // namespace daddk
+
+static int xb_splits(int BH, int N) {
+    int s = (2 * num_sms() + BH - 1) / BH;
+    const int max_s = (N + 2 * XB_ROWS - 1) / (2 * XB_ROWS);
+    if (s > max_s) s = max_s;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" int64_t dadd_cross_attn_bwd_workspace_bytes(int B, int H, int N, int d, int L) {
+    return (int64_t)2 * B * H * xb_splits(B * H, N) * L * d * sizeof(float);
+}
+
+extern "C" int dadd_cross_attn_bwd(const void* q, int64_t q_stride, const void* k_cat, const void* v_cat, const float* gates,
+                                   const void* dout, int64_t do_stride, void* dq, int64_t dq_stride, float* dk, float* dv,
+                                   float* workspace, int B, int H, int N, int d, int L, int seg_len, float scale, int dtype, void* stream) {
+    DADD_REQUIRE(q && k_cat && v_cat && gates && dout && dq && dk && dv && workspace, "dadd_cross_attn_bwd");
+    DADD_REQUIRE(dtype16_ok(dtype) && B >= 0 && H > 0 && N >= 0 && d > 0 && d <= 160, "dadd_cross_attn_bwd");
+    DADD_REQUIRE(seg_len > 0 && L % seg_len == 0 && L > 0 && L <= 48, "dadd_cross_attn_bwd");
+    DADD_REQUIRE(q_stride >= (int64_t)H * d && do_stride >= (int64_t)H * d && dq_stride >= (int64_t)H * d, "dadd_cross_attn_bwd");
+    if (B == 0 || N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int BH = B * H, splits = xb_splits(BH, N);
+    int rows = (N + splits - 1) / splits;
+    rows = (rows + XB_ROWS - 1) / XB_ROWS * XB_ROWS;
+    const size_t smem = ((size_t)2 * L * (d + 1) + 2 * XB_ROWS * (d + 1) + 2 * XB_ROWS * (L + 1)) * sizeof(float);
+    float* dk_part = workspace;
+    float* dv_part = workspace + (size_t)BH * splits * L * d;
+    DADD_DISPATCH_16(dtype, T, {
+        auto kern = cross_attn_bwd_kernel<T>;
+        if (smem > 48 * 1024 && cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dadd_cross_attn_bwd smem")) return 2;
+        kern<<<dim3(BH, splits), XB_THREADS, smem, s>>>((const T*)q, q_stride, (const T*)k_cat, (const T*)v_cat, gates, (const T*)dout, do_stride,
+                                                        (T*)dq, dq_stride, dk_part, dv_part, H, N, d, L, seg_len, scale, rows);
+    });
+    if (int rc = launched("dadd_cross_attn_bwd")) return rc;
+    const int64_t total = (int64_t)BH * L * d;
+    cross_attn_bwd_reduce_kernel<<<dim3((unsigned)((total + 255) / 256), 2), 256, 0, s>>>(dk_part, dv_part, dk, dv, total, L * d, splits);
+    return launched("dadd_cross_attn_bwd(reduce)");
+}

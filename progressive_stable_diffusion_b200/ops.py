@@ -426,6 +426,27 @@ def group_norm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, beta:
     return dx, dgamma, dbeta, dadd
 
 
+def cross_attention_bwd(q: torch.Tensor, k_cat: torch.Tensor, v_cat: torch.Tensor, gates: torch.Tensor, dout: torch.Tensor,
+                        heads: int, seg_len: int, n_seg: int):
+    """Backward of ``cross_attention``: (dq like q, dk_cat fp32, dv_cat fp32)."""
+    _cuda(q, k_cat, v_cat, gates, dout)
+    b, n, c = q.shape
+    d = c // heads
+    l = n_seg * seg_len
+    assert q.stride(-1) == 1 and dout.stride(-1) == 1 and dout.shape == q.shape and dout.dtype == q.dtype
+    assert k_cat.is_contiguous() and v_cat.is_contiguous() and k_cat.shape == (b, heads, l, d) == v_cat.shape and k_cat.dtype == q.dtype
+    assert gates.dtype == torch.float32 and gates.numel() >= n_seg
+    lib = _lib.load()
+    dq = torch.empty(b, n, c, dtype=q.dtype, device=q.device)
+    dk = torch.empty(b, heads, l, d, dtype=torch.float32, device=q.device)
+    dv = torch.empty_like(dk)
+    ws = torch.empty(max(int(lib.dadd_cross_attn_bwd_workspace_bytes(b, heads, n, d, l)), 8), dtype=torch.uint8, device=q.device)
+    _lib.check(lib.dadd_cross_attn_bwd(q.data_ptr(), q.stride(-2), k_cat.data_ptr(), v_cat.data_ptr(), gates.data_ptr(), dout.data_ptr(),
+                                       dout.stride(-2), dq.data_ptr(), c, dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), b, heads, n, d, l,
+                                       seg_len, float(d ** -0.5), _dt(q), _stream()), "dadd_cross_attn_bwd")
+    return dq, dk, dv
+
+
 def minsnr_mse(pred: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, need_grad: bool = True, upstream: float = 1.0):
     """loss = mean_b weight[b] * mean(pred[b] - target[b])^2 and (optionally) dloss/dpred * upstream, one pass."""
     _cuda(pred, target, weight)

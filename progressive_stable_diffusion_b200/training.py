@@ -8,9 +8,9 @@ What the reference does through Lightning (``/root/reference/src/models/diffusio
 
 * 16-bit (bf16 by default) channels-last activations, weights cast per step (the autocast policy of "16-mixed");
 * the memory-bound norm / gate layers and both attention cores on this package's CUDA kernels in forward, and hand-written
-  backward kernels for GroupNorm(+temb)(+SiLU), LayerNorm and GEGLU (``csrc/train.cu``); the attention cores recompute their
-  backward through the library flash-attention backward / a small fp32 einsum graph (the 48 condition tokens) - marked below;
-  convolutions and GEMMs are cuDNN / cuBLAS in both directions (off-path by the north-star);
+  backward kernels for GroupNorm(+temb)(+SiLU), LayerNorm, GEGLU and the triple-pathway cross-attention core
+  (``csrc/train.cu``); the self-attention core recomputes its backward through the library flash-attention backward - marked
+  below; convolutions and GEMMs are cuDNN / cuBLAS in both directions (off-path by the north-star);
 * the Min-SNR-weighted MSE loss and its gradient in one kernel;
 * data parallelism as one process per GPU: gradients live in flat fp32 buckets that are all-reduced (NCCL over NVLink) as soon
   as the backward pass has filled them, overlapped with the rest of backward; the three parameters the reference never uses in
@@ -118,9 +118,8 @@ class _SelfAttention(torch.autograd.Function):
 
 
 class _CrossAttention(torch.autograd.Function):
-    """Forward: the fused triple-pathway kernel (dadd_cross_attn_fwd: per-segment softmax, gate-weighted merge).  Backward:
-    the same arithmetic recomputed as an fp32 einsum graph over the <= 48 condition tokens (library GEMMs; 0.3 % of the step's
-    flops) - no hand-written kernel yet."""
+    """The fused triple-pathway core (per-segment softmax over the 16-token segments, gate-weighted merge):
+    dadd_cross_attn_fwd / dadd_cross_attn_bwd."""
 
     @staticmethod
     def forward(ctx, q, k_cat, v_cat, gates, heads: int, seg_len: int, n_seg: int):
@@ -132,19 +131,8 @@ class _CrossAttention(torch.autograd.Function):
     def backward(ctx, do):
         q, k_cat, v_cat, gates = ctx.saved_tensors
         heads, seg_len, n_seg = ctx.cfg
-        b, n, c = q.shape
-        d = c // heads
-        with torch.enable_grad():
-            qq = q.detach().float().reshape(b, n, heads, d).transpose(1, 2).requires_grad_(True)
-            kk, vv = k_cat.detach().float().requires_grad_(True), v_cat.detach().float().requires_grad_(True)
-            out = 0.0
-            for s in range(n_seg):
-                ks, vs = kk[:, :, s * seg_len:(s + 1) * seg_len], vv[:, :, s * seg_len:(s + 1) * seg_len]
-                p = torch.softmax(torch.matmul(qq, ks.transpose(-1, -2)) * (d ** -0.5), dim=-1)
-                out = out + gates[s] * torch.matmul(p, vs)
-            out = out.transpose(1, 2).reshape(b, n, c)
-            dq, dk, dv = torch.autograd.grad(out, (qq, kk, vv), do.float())
-        return dq.transpose(1, 2).reshape(b, n, c).to(q.dtype), dk.to(k_cat.dtype), dv.to(v_cat.dtype), None, None, None, None
+        dq, dk, dv = ops.cross_attention_bwd(q, k_cat, v_cat, gates, do.contiguous(), heads, seg_len, n_seg)
+        return dq, dk.to(k_cat.dtype), dv.to(v_cat.dtype), None, None, None, None
 
 
 # ================================================================================================ differentiable forward

@@ -92,6 +92,31 @@ def test_groupnorm_backward(shape, silu, with_add, dtype):
         assert (dadd.cpu() - ar.grad).abs().max().item() <= 2e-4 * scale + 1e-6
 
 
+@pytest.mark.parametrize("dtype", DT, ids=["bf16", "fp16"])
+@pytest.mark.parametrize("n,d,b,nseg", [(1024, 40, 2, 2), (256, 80, 2, 3), (64, 160, 3, 2), (16, 160, 2, 3), (100, 40, 1, 2), (333, 80, 1, 1)])
+def test_cross_attention_backward(n, d, b, nseg, dtype):
+    """dadd_cross_attn_bwd vs fp32 autograd of the reference arithmetic (routing_gates.py:148-178) on the same 16-bit inputs."""
+    ops = _ops()
+    h, seg = 8, 16
+    c, l = h * d, nseg * seg
+    g = torch.Generator().manual_seed(n + d + nseg)
+    q = (torch.randn(b, n, c, generator=g) * 1.2).to(dtype)
+    k, v = (torch.randn(b, h, l, d, generator=g) * 1.1).to(dtype), torch.randn(b, h, l, d, generator=g).to(dtype)
+    do = torch.randn(b, n, c, generator=g).to(dtype)
+    gates = torch.tensor([0.9, 0.1, 3.0])[:nseg]
+    qq, kk, vv = q.float().requires_grad_(True), k.float().requires_grad_(True), v.float().requires_grad_(True)
+    qh = qq.view(b, n, h, d).transpose(1, 2)
+    out = sum(gates[s] * torch.softmax(qh @ kk[:, :, s * seg:(s + 1) * seg].transpose(-1, -2) * d ** -0.5, -1) @ vv[:, :, s * seg:(s + 1) * seg]
+              for s in range(nseg))
+    out.transpose(1, 2).reshape(b, n, c).backward(do.float())
+    dq, dk, dv = ops.cross_attention_bwd(q.to(DEV), k.to(DEV), v.to(DEV), gates.to(DEV), do.to(DEV), h, seg, nseg)
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 2e-3
+    assert rel(dq, qq.grad) <= tol, rel(dq, qq.grad)
+    assert rel(dk, kk.grad) <= 1e-3 and rel(dv, vv.grad) <= 1e-3, (rel(dk, kk.grad), rel(dv, vv.grad))
+    again = ops.cross_attention_bwd(q.to(DEV), k.to(DEV), v.to(DEV), gates.to(DEV), do.to(DEV), h, seg, nseg)
+    assert all(torch.equal(a, b_) for a, b_ in zip((dq, dk, dv), again))
+
+
 def test_backward_kernels_are_bit_reproducible():
     ops = _ops()
     g = torch.Generator().manual_seed(11)
