@@ -30,7 +30,7 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change).  The host binding refuses a library whose
  * dadd_abi_version() differs from the DADD_ABI_VERSION it was written against. */
-#define DADD_ABI_VERSION 10
+#define DADD_ABI_VERSION 11
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -94,6 +94,12 @@ int dadd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, con
  * (dadd_groupnorm_cat_supported()).  Same kernels, path selection and workspace rule as dadd_groupnorm_fwd(NHWC) with
  * C = C1 + C2: workspace >= dadd_groupnorm_workspace_bytes(B, C1 + C2, HW, G, DADD_LAYOUT_NHWC). */
 int dadd_groupnorm_cat_supported(int B, int C1, int C2, int HW, int G, int dtype);
+/* Which NHWC 16-bit kernel dadd_groupnorm_fwd / dadd_groupnorm_cat_fwd take: 0 = the cluster / flat kernels above (default: the
+ * faster ones on B200 today, profiles/r02_groupnorm_stream.txt), 1 = the one-launch STREAMING kernel wherever it serves the shape
+ * (C1, C2 % 64 == 0, HW % 16 == 0, G even; persistent CTAs, TMA slab ring, tensor-core statistics, per-group partial sums exchanged
+ * through `workspace` behind release flags that carry a device-side launch generation; csrc/groupnorm_stream.cu).  Process-wide;
+ * returns the previous value.  The environment variable DADD_GN_IMPL=stream selects 1 at load time. */
+int dadd_groupnorm_select(int impl);
 int dadd_groupnorm_cat_fwd(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
                            const float* chan_add /* nullable */, int64_t chan_add_stride, void* y, int B, int HW, int G,
                            float eps, int apply_silu, int dtype /* DADD_BF16 | DADD_F16 */, void* workspace,

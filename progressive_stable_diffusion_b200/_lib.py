@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DADD_B200_LIB") or os.path.join(HERE, "libdadd_b200.s
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
-ABI_VERSION = 10         # == DADD_ABI_VERSION of include/dadd_b200.h that SIGNATURES below was written against
+ABI_VERSION = 11         # == DADD_ABI_VERSION of include/dadd_b200.h that SIGNATURES below was written against
 
 # name -> argtypes; mirrors include/dadd_b200.h one to one (tests/test_abi.py checks header <-> table <-> .so)
 SIGNATURES = {
@@ -24,6 +24,7 @@ SIGNATURES = {
     "dadd_groupnorm_workspace_bytes": [_I, _I, _I, _I, _I],
     "dadd_groupnorm_fwd": [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _P, _L, _P],
     "dadd_groupnorm_cat_supported": [_I, _I, _I, _I, _I, _I],
+    "dadd_groupnorm_select": [_I],
     "dadd_groupnorm_cat_fwd": [_P, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P],
     "dadd_layernorm_fwd": [_P, _P, _P, _P, _L, _I, _F, _I, _P],
     "dadd_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],

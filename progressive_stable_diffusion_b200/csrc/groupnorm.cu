@@ -668,9 +668,19 @@ __global__ void __launch_bounds__(512) gn_nchw_kernel(const T* __restrict__ x, c
     }
 }
 
+// groupnorm_stream.cu: the one-launch streaming kernel (16-bit NHWC); -1 = shape not served
+int64_t gn_stream_workspace_bytes(int B, int C, int HW, int G);
+template <typename T>
+int gn_stream_launch(const T* x, const T* x2, int C1, const float* gamma, const float* beta, const float* chan_add, int64_t add_stride,
+                     T* y, int B, int C, int HW, int G, float eps, int act, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+
+static std::atomic<int> g_gn_impl{[] { const char* e = getenv("DADD_GN_IMPL"); return (e && !strcmp(e, "stream")) ? 1 : 0; }()};
+
 static int64_t gn_workspace_bytes(int B, int C, int HW, int G) {
     const GnPlan p = gn_plan(B, C, HW);
-    return (int64_t)B * p.chunks * G * sizeof(float2) + (int64_t)B * 2 * C * sizeof(float);
+    const int64_t flat = (int64_t)B * p.chunks * G * sizeof(float2) + (int64_t)B * 2 * C * sizeof(float);
+    const int64_t stream = gn_stream_workspace_bytes(B, C, HW, G);
+    return flat > stream ? flat : stream;
 }
 
 // The one-launch cluster kernel serves every shape it can hold; the flat passes (stats [-> final] -> apply) take the rest (samples
@@ -689,6 +699,12 @@ template <typename T>
 static int launch_nhwc(const T* x, const T* x2, int C1, const float* gamma, const float* beta, const float* chan_add, int64_t add_stride,
                        T* y, int B, int C, int HW, int G, float eps, int silu, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
     DADD_REQUIRE(C / 8 <= 512, "dadd_groupnorm_fwd(NHWC)");
+    if constexpr (sizeof(T) == 2) {
+        if (g_gn_impl.load(std::memory_order_relaxed) == 1) {      // dadd_groupnorm_select(1) / DADD_GN_IMPL=stream
+            const int rc = gn_stream_launch<T>(x, x2, C1, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, workspace, workspace_bytes, s);
+            if (rc >= 0) return rc;
+        }
+    }
     const GncPlan cp = gnc_plan(B, C, HW, G, sizeof(T));
     if (!gn_use_flat(cp, B, C, HW, sizeof(T))) return launch_cluster(cp, x, x2, C1, gamma, beta, chan_add, add_stride, y, B, C, HW, G, eps, silu, s);
     DADD_REQUIRE(workspace != nullptr && workspace_bytes >= gn_workspace_bytes(B, C, HW, G), "dadd_groupnorm_fwd(NHWC)");
@@ -762,6 +778,8 @@ extern "C" int dadd_groupnorm_fwd(const void* x, const float* gamma, const float
     DADD_DISPATCH_ANY(dtype, T, return launch_nchw((const T*)x, gamma, beta, chan_add, chan_add_stride, (T*)y, B, C, HW, G, eps, apply_silu, s));
     return 1;
 }
+
+extern "C" int dadd_groupnorm_select(int impl) { return g_gn_impl.exchange(impl == 1 ? 1 : 0); }
 
 extern "C" int dadd_groupnorm_cat_supported(int B, int C1, int C2, int HW, int G, int dtype) {
     return (B > 0 && C1 > 0 && C2 > 0 && HW > 0 && G > 0 && G <= GN_MAX_G && C1 % 8 == 0 && C2 % 8 == 0 && (C1 + C2) % G == 0 &&

@@ -200,6 +200,72 @@ def test_groupnorm_nhwc_many_chunks_and_reproducible(b, c, hw):
     assert (y1.float().cpu() - ref).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("b,c,hw,dtype", [(104, 320, 32, torch.float16), (30, 640, 16, torch.bfloat16), (150, 1280, 4, torch.float16),
+                                          (7, 2560, 8, torch.float16), (2, 320, 64, torch.float16)])
+def test_groupnorm_streaming_kernel_many_items_graph_replay(b, c, hw, dtype):
+    """The one-launch streaming kernel (persistent CTAs, flag-published partial sums, device-side launch generation): many
+    items per CTA, samples whose slabs straddle rounds, repeated launches and a captured graph replayed several times must all give
+    the same bits, and match fp32 GroupNorm.  (Opt-in through dadd_groupnorm_select(1): the cluster kernel is still the faster one.)"""
+    ops = _ops()
+    from progressive_stable_diffusion_b200 import _lib
+    prev = _lib.load().dadd_groupnorm_select(1)
+    try:
+        _streaming_case(ops, b, c, hw, dtype)
+    finally:
+        _lib.load().dadd_groupnorm_select(prev)
+
+
+def _streaming_case(ops, b, c, hw, dtype):
+    g = torch.Generator().manual_seed(b + c + hw)
+    x = (torch.randn(b, c, hw, hw, generator=g) * 1.7 - 0.9).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    gamma, beta = (1 + 0.2 * torch.randn(c, generator=g)).to(DEV), (0.2 * torch.randn(c, generator=g)).to(DEV)
+    add = torch.randn(b, c, generator=g).to(DEV)
+    ys = [ops.group_norm(x, gamma, beta, 32, 1e-5, True, add) for _ in range(3)]
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
+    out = torch.empty_like(x)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        ops.group_norm(x, gamma, beta, 32, 1e-5, True, add, out=out)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            ops.group_norm(x, gamma, beta, 32, 1e-5, True, add, out=out)
+            ops.group_norm(x, gamma, beta, 32, 1e-5, True, add, out=out)
+        for _ in range(3):
+            out.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, ys[0])
+    sel = slice(0, min(b, 4))
+    ref = F.silu(F.group_norm(x[sel].float().cpu() + add[sel].cpu()[:, :, None, None], 32, gamma.cpu(), beta.cpu(), 1e-5))
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    assert (ys[0][sel].float().cpu() - ref).abs().max().item() <= ulp * max(1.0, ref.abs().max().item())
+
+
+
+@pytest.mark.parametrize("c1,c2,hw,b", [(1280, 640, 8, 9), (640, 320, 32, 26), (320, 320, 32, 3)])
+def test_groupnorm_streaming_kernel_two_sources(c1, c2, hw, b):
+    """Streaming kernel on [x1 | x2]: bit-equal to the same kernel on the materialised concatenation, and within an fp16 ulp of fp32."""
+    ops = _ops()
+    from progressive_stable_diffusion_b200 import _lib
+    g = torch.Generator().manual_seed(c1 + c2 + hw)
+    x1 = (torch.randn(b, c1, hw, hw, generator=g) * 1.5 + 0.7).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    x2 = (torch.randn(b, c2, hw, hw, generator=g) * 0.6 - 0.4).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    c = c1 + c2
+    gamma, beta = (1 + 0.2 * torch.randn(c, generator=g)).to(DEV), (0.2 * torch.randn(c, generator=g)).to(DEV)
+    add = torch.randn(b, c, generator=g).to(DEV)
+    cat = torch.cat([x1, x2], dim=1).contiguous(memory_format=torch.channels_last)
+    prev = _lib.load().dadd_groupnorm_select(1)
+    try:
+        want = ops.group_norm(cat, gamma, beta, 32, 1e-5, True, add)
+        got = ops.group_norm_cat(x1, x2, gamma, beta, 32, 1e-5, True, add)
+    finally:
+        _lib.load().dadd_groupnorm_select(prev)
+    assert torch.equal(got, want)
+    ref = F.silu(F.group_norm(cat.float().cpu() + add.cpu()[:, :, None, None], 32, gamma.cpu(), beta.cpu(), 1e-5))
+    assert (got.float().cpu() - ref).abs().max().item() <= 2.0 ** -10 * max(1.0, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm / GEGLU
 @pytest.mark.parametrize("rows", [1, 7, 1024 * 3 + 5])
 @pytest.mark.parametrize("c", [320, 640, 1280, 768, 2048, 8])
