@@ -188,7 +188,8 @@ int dadd_cross_attn_fwd(const void* q, int64_t q_stride, const void* k_cat, cons
  * Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0, installed by
  * src/models/attention_processor_routing_gates.py:284-286 and attention_processor_base.py:196-197.
  * q, k, v: 16-bit (`dtype`: DADD_BF16 | DADD_F16) [B][N][*] with row strides (elements); head h at column h*d (so the
- * three can alias one fused [B][N][3C] projection output); o: same dtype and convention.  d % 8 == 0, d <= 160.
+ * three can alias one fused [B][N][3C] projection output); o: same dtype and convention.  d % 8 == 0, d <= 160 - or d = 256 / 512: wide single
+ * heads (the VAE mid block's attention, src/models/vae/vae.py:90-112) on a column-split mma.sync kernel, any N, `impl` ignored.
  * impl: 0 = shape dispatch (N >= 128 -> tcgen05/TMEM/TMA flash kernel, else warp-level mma.sync kernel),
  *       1 = force mma.sync, 2 = force tcgen05 (N >= 128 required).
  */

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .unet2d import CL, ResnetBlock2D, Upsample2D, _Block, _conv, _gn, _linear, Attention
 
 
@@ -73,7 +74,7 @@ def _mid_attention(a: Attention, x: torch.Tensor) -> torch.Tensor:
     b, c, h, w = x.shape
     t = _gn(a.group_norm, x, silu=False).permute(0, 2, 3, 1).reshape(b, h * w, c)
     q, k, v = _linear(a.to_q, t), _linear(a.to_k, t), _linear(a.to_v, t)
-    o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+    o = ops.self_attention(q, k, v, heads=1)          # one 512-wide head: dadd_self_attn_fwd's wide-head kernel
     return x + _linear(a.to_out[0], o).view(b, h, w, c).permute(0, 3, 1, 2)
 
 

@@ -435,6 +435,25 @@ def test_self_attention_core(n, d, b, impl, dtype):
     assert rel_err(o, ref) <= tol, rel_err(o, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("n,d,h,b", [(1024, 512, 1, 2), (1000, 512, 1, 1), (77, 512, 1, 3), (256, 256, 2, 2), (4096, 512, 1, 1)])
+def test_self_attention_wide_heads(n, d, h, b, dtype):
+    """d = 256 / 512 (the VAE mid block's single head): the column-split mma.sync kernel against fp32 SDPA, ragged N included,
+    q / k / v as strided views of one fused buffer and growing row maxima along the keys."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + d)
+    c = h * d
+    qkv = (torch.randn(b, n, 3 * c, generator=g) * 0.35).to(dtype)
+    qkv[..., c:2 * c] *= torch.linspace(0.5, 2.0, n)[None, :, None].to(dtype)       # later keys score higher: rescales on most tiles
+    q, k, v = (qkv[..., i * c:(i + 1) * c].float().view(b, n, h, d).transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+    qd = qkv.to(DEV)
+    o = ops.self_attention(qd[..., :c], qd[..., c:2 * c], qd[..., 2 * c:], h)
+    torch.cuda.synchronize()
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 3e-3
+    assert rel_err(o, ref) <= tol, rel_err(o, ref)
+
+
 @pytest.mark.parametrize("n,d,b", [(1024, 40, 26), (640, 80, 20), (256, 64, 40), (256, 80, 40), (256, 160, 24), (128, 40, 60)])
 def test_self_attention_persistent_many_items_and_growing_maxima(n, d, b):
     """More work items than SMs (every persistent CTA walks several), and scores whose row maxima keep growing along the
