@@ -147,7 +147,9 @@ int dadd_geglu_fwd(const void* x, void* y, int64_t rows, int inner, int dtype, v
  * with the residual adds that follow them (`ff(x) + x`, `proj_out(x) + residual`, `shortcut(x) + h`).
  * x: [M][K], w: [N][K] (nn.Linear layout), y / residual: [M][N], all 16-bit `dtype`, dense rows, 16-byte aligned; bias: fp32 [N]
  * (nullable); residual nullable and may alias y.  The product is rounded to 16 bits before the residual is added (as the
- * unfused GEMM + add).  K % 8 == 0 and N a multiple of 160 or 256: dadd_linear_supported() says whether a shape qualifies. */
+ * unfused GEMM + add).  K % 8 == 0 and N % 64 == 0: dadd_linear_supported() says whether a shape qualifies.  Persistent tcgen05
+ * GEMM, tiles 128 x {256, 192, 128}; from K = 512 on the CTAs run as pairs (cta_group::2: M = 256 MMAs over both CTAs' shared memory
+ * and TMEM).  Measured 4-17 % behind cuBLAS on the UNet's shapes (profiles/r02_linear_gemm.txt): the host keeps cuBLAS as its default. */
 int dadd_linear_supported(int64_t M, int N, int K);
 int dadd_linear_fwd(const void* x, const void* w, const float* bias /* nullable */, const void* residual /* nullable */, void* y,
                     int64_t M, int N, int K, int dtype /* DADD_BF16 | DADD_F16 */, void* stream);

@@ -6,13 +6,17 @@
 // proj_out fused with the block residual.  The shapes are short-K (K = 320 .. 1280 for most of them), where a GEMM is bound
 // by its epilogue: the accumulator is double-buffered in TMEM so that tile i + 1 is multiplied while tile i drains.
 //
+// CTAs run as PAIRS (cluster of two, tcgen05 cta_group::2) on one 256-row x BN-column tile: each CTA loads its own 128 rows of X and
+// HALF of the W tile (BN / 2 rows); the pair's leader issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs'
+// TMEM.  What bounds these short-K GEMMs on B200 is the bytes an SM takes in per flop (~45 B/clk per SM measured: the one-CTA form
+// ingests 16 + BN / 8 KB per K-block and lost 10-25 % to cuBLAS; TMA-multicasting W to both CTAs changed nothing - every SM still
+// ingests the whole W tile; profiles/r01_linear_gemm.txt, r02_linear_gemm.txt); the pair form ingests 16 + BN / 16 KB.
 //   warp 8     TMA producer: ring of K-blocks {X 128 x 64, W BN x 64}, 128-byte swizzle, zero-filled edges;
 //   warp 9     one elected thread issues tcgen05.mma (SS, M128 x N=BN x K16) into accumulator (i & 1);
-//   warps 0-7  epilogue in two phases.  (1) row owners (TMEM lane == row; warps 0-3 / 4-7 take the two column halves):
-//              tcgen05.ld -> + bias -> 16-bit -> padded staging tile in shared memory;  (2) all 256 threads walk the staging
-//              tile in row-major 16-byte chunks: (+ residual chunk, coalesced) -> coalesced 16-byte global stores.  The
-//              result is rounded to 16 bits before the residual is added, exactly like the unfused GEMM + add it replaces.
-// BN = 256 when N % 256 == 0, else 160 (N = 320, 640, 960, 1920 are multiples of 160).
+//   warps 0-7  epilogue, two groups of four warps (TMEM lane == row): group g takes the 64-column chunks g, g + 2 of the tile:
+//              tcgen05.ld -> + bias -> 16 bits (+ residual, read straight from global memory) -> swizzled staging panel -> TMA store.
+//              The result is rounded to 16 bits before the residual is added, exactly like the unfused GEMM + add it replaces.
+// BN = 256 / 192 when N is a multiple, else 128 (N % 64 == 0 required; edge tiles are clipped by the tensor maps).
 #include <cstdlib>
 
 #include "tc_util.cuh"
@@ -45,6 +49,55 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// ---- CTA-pair (cta_group::2) forms: the leader's MMA reads both CTAs' shared memory and writes both CTAs' TMEM
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -52,49 +105,60 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
-template <typename T, int BN, int STAGES>
+template <typename T, int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
-linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CUtensorMap tw, const float* __restrict__ bias,
-              const T* __restrict__ res, T* __restrict__ y, int M, int N, int K) {
+linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CUtensorMap tw, const __grid_constant__ CUtensorMap ty,
+              const float* __restrict__ bias, const T* __restrict__ res, int M, int N, int K) {
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t FMT = std::is_same_v<T, __nv_bfloat16> ? 1u : 0u;
-    constexpr uint32_t IDESC = instr_desc(FMT, BN, 0);
-    constexpr uint32_t B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int PITCH = BN * 2 + 16;                            // staging row pitch (bytes): conflict-free 16-byte row-owner stores
-    constexpr int HALF = BN / 2;                                  // columns per epilogue warp group
-    constexpr int CHUNKS = BN / 8;                                // 16-byte chunks per staging row
-    static_assert(BN % 32 == 0 && BN <= 256, "tile width");
+    // M = 256 over the CTA pair (bits 24-28 of the instruction descriptor hold M >> 4), N = BN: each CTA supplies 128 rows of X and BN / 2 rows of W
+    // (PAIR = false: every CTA is its own tile of 128 rows, cta_group::1 - the form short K = 320 GEMMs run fastest in.)
+    constexpr uint32_t IDESC = PAIR ? ((instr_desc(FMT, BN, 0) & ~(0x1Fu << 24)) | ((256u >> 4) << 24)) : instr_desc(FMT, BN, 0);
+    constexpr uint32_t B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int NCH = BN / 64;                                  // 64-column output chunks per tile
+    constexpr uint32_t OUT_PANEL = 128 * 128;                     // 128 rows x 64 16-bit columns, 128-byte swizzle
+    static_assert(BN % 64 == 0 && BN <= 256, "tile width");
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sStage = smem;                                 // [STAGES]{X, W}
-    unsigned char* sOut = sStage + STAGES * STAGE_BYTES;          // [128][PITCH]
-    float* sBias = reinterpret_cast<float*>(sOut + BMR * PITCH);  // [BN]
-    Bars<STAGES>* bars = reinterpret_cast<Bars<STAGES>*>(sBias + BN);
+    unsigned char* sOut = sStage + STAGES * STAGE_BYTES;          // [2 warp groups][2 panels]
+    float* sBias = reinterpret_cast<float*>(sOut + 4 * OUT_PANEL);  // [2 accumulators][BN]
+    Bars<STAGES>* bars = reinterpret_cast<Bars<STAGES>*>(sBias + 2 * BN);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = (M + BMR - 1) / BMR, nt = N / BN;
-    const int tiles = mt * nt;
-    const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // PAIR: cluster = CTA pair on two adjacent row blocks; else every CTA stands alone ("cluster" = CTA, rank 0, one row block per tile)
+    const int rank = PAIR ? (int)cluster_rank() : 0, cluster = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+    const int nclusters = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+    constexpr int TROWS = PAIR ? 2 * BMR : BMR;
+    const int nt = (N + BN - 1) / BN;
+    const int pairs = ((M + TROWS - 1) / TROWS) * nt;
+    const int my_tiles = (pairs - cluster + nclusters - 1) / nclusters;
     const int kblocks = (K + BK - 1) / BK;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->empty[s], 1);                            // the leader's commit, multicast to both CTAs
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], 256);
+            mbar_init(&bars->acc_empty[a], PAIR ? 512 : 256);         // (PAIR: the leader's is the one in use) both CTAs' epilogue threads
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync();                               // the peer's barriers exist before anything is signalled across
     fence_after();
     const uint32_t tmem = bars->tmem_base;
 
@@ -104,15 +168,22 @@ linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CU
             // block are read by neighbouring CTAs at the same time and hit L2; W is L2-resident throughout)
             uint32_t it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-                const int m0 = (tile / nt) * BMR, n0 = (tile % nt) * BN;
+                const int pair = cluster + i * nclusters;
+                const int m0 = (pair / nt) * TROWS + rank * BMR, n0 = (pair % nt) * BN;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t st = it % STAGES;
                     mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&bars->full[st], STAGE_BYTES);
                     const uint32_t base = smem_u32(sStage + st * STAGE_BYTES);
-                    tma_load_2d(base, &tx, &bars->full[st], kb * BK, m0);
-                    tma_load_2d(base + A_BYTES, &tw, &bars->full[st], kb * BK, n0);
+                    if constexpr (PAIR) {
+                        if (rank == 0) mbar_expect_tx(&bars->full[st], 2 * STAGE_BYTES);   // both CTAs' loads complete on the leader's barrier
+                        const uint32_t lbar = map_to_rank(smem_u32(&bars->full[st]), 0);
+                        tma_load_2d_pair(base, &tx, lbar, kb * BK, m0);
+                        tma_load_2d_pair(base + A_BYTES, &tw, lbar, kb * BK, n0 + rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(&bars->full[st], STAGE_BYTES);
+                        tma_load_2d(base, &tx, &bars->full[st], kb * BK, m0);
+                        tma_load_2d(base + A_BYTES, &tw, &bars->full[st], kb * BK, n0);
+                    }
                 }
             }
         }
@@ -120,9 +191,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CU
         // ---------------------------------------------------------------------- MMA issuer
         const bool leader = elect_one();
         uint32_t it = 0;
-        for (int i = 0; i < my_tiles; ++i) {
+        for (int i = 0; i < (rank == 0 ? my_tiles : 0); ++i) {                   // the pair's leader issues for both CTAs
             const int a = i & 1;
-            if (i >= 2) mbar_wait(&bars->acc_empty[a], ((i >> 1) - 1) & 1);      // the epilogue has drained this accumulator
+            if (i >= 2) mbar_wait(&bars->acc_empty[a], ((i >> 1) - 1) & 1);      // both epilogues have drained this accumulator
             fence_after();
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t st = it % STAGES;
@@ -133,77 +204,98 @@ linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CU
                     const uint64_t da = smem_desc(base, 16, 1024), db = smem_desc(base + A_BYTES, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        mma_ss(tmem + a * 256, desc_add(da, k * 32), desc_add(db, k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-                    mma_commit(&bars->empty[st]);
-                    if (kb + 1 == kblocks) mma_commit(&bars->acc_full[a]);
+                        if constexpr (PAIR) mma_ss_pair(tmem + a * 256, desc_add(da, k * 32), desc_add(db, k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                        else mma_ss(tmem + a * 256, desc_add(da, k * 32), desc_add(db, k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                    if constexpr (PAIR) {
+                        mma_commit_pair(&bars->empty[st]);
+                        if (kb + 1 == kblocks) mma_commit_pair(&bars->acc_full[a]);
+                    } else {
+                        mma_commit(&bars->empty[st]);
+                        if (kb + 1 == kblocks) mma_commit(&bars->acc_full[a]);
+                    }
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ---------------------------------------------------------------------- epilogue (8 warps)
-        const int half = warp >> 2;
+        // ---------------------------------------------------------------------- epilogue (two groups of four warps)
+        // Group g takes the 64-column chunks g, g + 2 of the tile: TMEM row -> + bias -> 16 bits (+ residual) -> one of the group's two
+        // swizzled staging panels -> TMA store (rows beyond M and columns beyond N are clipped by the tensor map).  A panel is
+        // rewritten once the store issued from it two chunks ago has been read out of shared memory.
+        const int group = warp >> 2;
         const int row = (warp & 3) * 32 + lane;                       // row inside the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const bool store_leader = (tid & 127) == 0;
+        uint32_t pc = 0;                                              // chunks this group has staged so far
         for (int i = 0; i < my_tiles; ++i) {
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-            const int m0 = (tile / nt) * BMR, n0 = (tile % nt) * BN;
+            const int pair = cluster + i * nclusters;
+            const int m0 = (pair / nt) * TROWS + rank * BMR, n0 = (pair % nt) * BN;
             const int a = i & 1;
-            if (tid < BN) sBias[tid] = bias ? bias[n0 + tid] : 0.0f;
+            float* bs = sBias + a * BN;
+            if (tid < BN) bs[tid] = (bias && n0 + tid < N) ? bias[n0 + tid] : 0.0f;      // (slot last read two tiles ago)
             mbar_wait(&bars->acc_full[a], (i >> 1) & 1);
             fence_after();
-            named_sync(1, 256);                                       // bias staged; phase 2 of the previous tile has left sOut
-            // ---- phase 1: accumulator row -> + bias -> 16-bit -> staging
-            const uint32_t tacc = tmem + a * 256 + half * HALF + lane_base;
-            unsigned char* srow = sOut + row * PITCH + half * HALF * 2;
-            const float* bs = sBias + half * HALF;
-#pragma unroll
-            for (int c = 0; c < HALF; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(tacc + c, v);
-                tmem_wait_ld();
-                if (c + 16 == HALF) {                                 // accumulator fully read: hand it back to the MMA warp
-                    fence_before();
-                    mbar_arrive(&bars->acc_empty[a]);
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(bs + c + j * 8), b1 = *reinterpret_cast<const float4*>(bs + c + j * 8 + 4);
-                    uint4 out;
-                    out.x = pack2<T>(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
-                    out.y = pack2<T>(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
-                    out.z = pack2<T>(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
-                    out.w = pack2<T>(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
-                    *reinterpret_cast<uint4*>(srow + (c + j * 8) * 2) = out;
-                }
-            }
             named_sync(1, 256);
-            // ---- phase 2: row-major 16-byte chunks: (+ residual) -> coalesced global stores
-            const int rows = min(BMR, M - m0);
-            for (int idx = tid; idx < rows * CHUNKS; idx += 256) {
-                const int r = idx / CHUNKS, j = idx - r * CHUNKS;
-                Vec8<T> t;
-                t.raw = *reinterpret_cast<const uint4*>(sOut + r * PITCH + j * 16);
-                const size_t g = (size_t)(m0 + r) * N + n0 + j * 8;
-                if (res) {
-                    Vec8<T> rr;
-                    rr.load(res + g);
-                    float f[8], q[8];
-                    t.unpack(f);
-                    rr.unpack(q);
+            const bool row_ok = m0 + row < M;
+#pragma unroll 1
+            for (int c = group; c < NCH; c += 2, ++pc) {
+                unsigned char* panel = sOut + (group * 2 + (pc & 1)) * OUT_PANEL;
+                if (store_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                named_sync(2 + group, 128);
+                uint32_t v[64];
+                tmem_ld32(tmem + a * 256 + c * 64 + lane_base, *reinterpret_cast<uint32_t(*)[32]>(v));
+                tmem_ld32(tmem + a * 256 + c * 64 + 32 + lane_base, *reinterpret_cast<uint32_t(*)[32]>(v + 32));
+                uint4 rr[8];
+                const bool col_ok = n0 + c * 64 < N;                  // N % 64 == 0: a chunk is inside or outside as a whole
+                if (res && row_ok && col_ok) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)(m0 + row) * N + n0 + c * 64);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] += q[e];
-                    t.pack(f);
+                    for (int j = 0; j < 8; ++j) rr[j] = rp[j];
                 }
-                t.store(y + g);
+                tmem_wait_ld();
+                if (c + 2 >= NCH) {                                   // my last read of this accumulator: hand it back to the MMA warp
+                    fence_before();
+                    if (rank == 0) mbar_arrive(&bars->acc_empty[a]);
+                    else mbar_arrive_remote(map_to_rank(smem_u32(&bars->acc_empty[a]), 0));
+                }
+                const float* bc = bs + c * 64;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bc + j * 8), b1 = *reinterpret_cast<const float4*>(bc + j * 8 + 4);
+                    Vec8<T> t;
+                    t.raw.x = pack2<T>(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
+                    t.raw.y = pack2<T>(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
+                    t.raw.z = pack2<T>(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
+                    t.raw.w = pack2<T>(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
+                    if (res && row_ok && col_ok) {                    // (product rounded to 16 bits first, like the unfused GEMM + add)
+                        Vec8<T> q;
+                        q.raw = rr[j];
+                        float f[8], g[8];
+                        t.unpack(f);
+                        q.unpack(g);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] += g[e];
+                        t.pack(f);
+                    }
+                    *reinterpret_cast<uint4*>(panel + row * 128 + ((j ^ (row & 7)) << 4)) = t.raw;      // 128-byte swizzle
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_sync(2 + group, 128);
+                if (store_leader) {
+                    tma_store_2d(&ty, smem_u32(panel), n0 + c * 64, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
         }
+        if (store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync();                               // no CTA leaves while its peer may still signal its barriers
     if (warp == 9) {
         fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
     }
 }
 
@@ -222,17 +314,41 @@ static int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t
     return 0;
 }
 
-template <typename T, int BN, int STAGES>
+template <typename T, int BN, int STAGES, bool PAIR>
 static int launch(const void* x, const void* w, const float* bias, const void* res, void* y, int64_t M, int N, int K, int dtype,
                   cudaStream_t s) {
-    CUtensorMap tx, tw;
-    if (make_map_2d(&tx, x, M, K, dtype, BMR) || make_map_2d(&tw, w, N, K, dtype, BN)) return 1;
-    const size_t smem = (size_t)STAGES * (A_BYTES + BN * BK * 2) + (size_t)BMR * (BN * 2 + 16) + BN * sizeof(float) + sizeof(Bars<STAGES>) + 1024;
-    const int64_t tiles = ((M + BMR - 1) / BMR) * (N / BN);
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    auto kern = linear_kernel<T, BN, STAGES>;
+    CUtensorMap tx, tw, ty;
+    if (make_map_2d(&tx, x, M, K, dtype, BMR) || make_map_2d(&tw, w, N, K, dtype, PAIR ? BN / 2 : BN) || make_map_2d(&ty, y, M, N, dtype, BMR)) return 1;
+    const size_t smem = (size_t)STAGES * (A_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + (size_t)4 * 128 * 128 + 2 * BN * sizeof(float) + sizeof(Bars<STAGES>) + 1024;
+    const int64_t pairs = ((M + (PAIR ? 2 : 1) * BMR - 1) / ((PAIR ? 2 : 1) * BMR)) * ((N + BN - 1) / BN);
+    auto kern = linear_kernel<T, BN, STAGES, PAIR>;
     if (cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "linear smem")) return 2;
-    kern<<<grid, NTHREADS, smem, s>>>(tx, tw, bias, (const T*)res, (T*)y, (int)M, N, K);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(NTHREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    static int max_clusters = 0;                       // co-resident CTA pairs / CTAs (one CTA per SM): the persistent grid (per instance)
+    if (max_clusters == 0) {
+        if (PAIR) {
+            cfg.gridDim = dim3(num_sms() & ~1, 1, 1);
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = num_sms() / 2;
+        } else {
+            max_clusters = num_sms();
+        }
+    }
+    const int clusters = (int)(pairs < max_clusters ? pairs : max_clusters);
+    cfg.gridDim = dim3((PAIR ? 2 : 1) * clusters, 1, 1);
+    const int Mi = (int)M;
+    const T* resT = (const T*)res;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, bias, resT, Mi, N, K);
+    if (e != cudaSuccess) return cuda_ok(e, "dadd_linear_fwd launch");
     return launched("dadd_linear_fwd");
 }
 
@@ -241,7 +357,7 @@ static int launch(const void* x, const void* w, const float* bias, const void* r
 
 using namespace daddk;
 
-extern "C" int dadd_linear_supported(int64_t M, int N, int K) { return (M > 0 && K > 0 && K % 8 == 0 && N > 0 && (N % 256 == 0 || N % 160 == 0)) ? 1 : 0; }
+extern "C" int dadd_linear_supported(int64_t M, int N, int K) { return (M > 0 && K > 0 && K % 8 == 0 && N > 0 && N % 64 == 0) ? 1 : 0; }
 
 extern "C" int dadd_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y, int64_t M, int N, int K,
                                int dtype, void* stream) {
@@ -250,10 +366,22 @@ extern "C" int dadd_linear_fwd(const void* x, const void* w, const float* bias, 
     DADD_REQUIRE(M >= 0 && M < (1ll << 31) - 128, "dadd_linear_fwd");
     if (M == 0) return 0;
     if (!dadd_linear_supported(M, N, K))
-        return fail("%s: needs K %% 8 == 0 and N a multiple of 160 or 256 (N = %lld, K = %lld)", "dadd_linear_fwd", (long long)N, (long long)K);
+        return fail("%s: needs K %% 8 == 0 and N %% 64 == 0 (N = %lld, K = %lld)", "dadd_linear_fwd", (long long)N, (long long)K);
     DADD_REQUIRE(((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)residual) % 16 == 0, "dadd_linear_fwd");
     cudaStream_t s = (cudaStream_t)stream;
-    if (N % 256 == 0) DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 256, 3>(x, w, bias, residual, y, M, N, K, dtype, s)));
-    DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 160, 4>(x, w, bias, residual, y, M, N, K, dtype, s)));
+    // tile width: 256 / 192 where N is a multiple, else 128 (N = 320: the third tile is half empty; the tensor maps clip it)
+    static const int force_bn = [] { const char* e = getenv("DADD_LIN_BN"); return e ? atoi(e) : 0; }();
+    static const int force_pair = [] { const char* e = getenv("DADD_LIN_PAIR"); return e ? atoi(e) : -1; }();
+    const int bn = force_bn ? force_bn : (N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128));
+    // CTA pairs (cta_group::2) pay a cross-CTA hand-off per tile: they win from K = 640 on, short K = 320 tiles run faster alone
+    const bool pair = force_pair >= 0 ? force_pair != 0 : K >= 512;
+    if (pair) {
+        if (bn == 256) DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 256, 4, true>(x, w, bias, residual, y, M, N, K, dtype, s)));
+        if (bn == 192) DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 192, 4, true>(x, w, bias, residual, y, M, N, K, dtype, s)));
+        DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 128, 6, true>(x, w, bias, residual, y, M, N, K, dtype, s)));
+    }
+    if (bn == 256) DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 256, 3, false>(x, w, bias, residual, y, M, N, K, dtype, s)));
+    if (bn == 192) DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 192, 3, false>(x, w, bias, residual, y, M, N, K, dtype, s)));
+    DADD_DISPATCH_16(dtype, T, return (lin::launch<T, 128, 4, false>(x, w, bias, residual, y, M, N, K, dtype, s)));
     return 1;
 }

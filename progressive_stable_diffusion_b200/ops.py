@@ -223,8 +223,9 @@ def geglu(x: torch.Tensor) -> torch.Tensor:
 
 
 # Which GEMM ``linear(..., impl="auto")`` runs: "lib" = cuBLAS (+ one fused bias / residual pass), "tc" = dadd_linear_fwd where
-# the shape qualifies.  Measured on B200 (profiles/r01_linear_gemm.txt): the one-CTA 128 x 160/256 tiles of dadd_linear_fwd
-# re-read their operands from L2 too often and lose 10-25 % to cuBLAS' two-CTA 256-wide tiles, so the default is "lib".
+# the shape qualifies.  Measured on B200: round 1's one-CTA kernel lost 10-25 % to cuBLAS (profiles/r01_linear_gemm.txt); round 2's
+# CTA-pair (cta_group::2) kernel with a TMA-store epilogue is 4-17 % behind on the UNet's shapes and far behind at M < 2000
+# (profiles/r02_linear_gemm.txt), so the default is still "lib".
 LINEAR_IMPL = "lib"
 
 
@@ -239,8 +240,8 @@ def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
            out: Optional[torch.Tensor] = None, impl: str = "auto", bias_lp: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.linear(x, w, bias) (+ residual)``: x (..., K) 16-bit, w (N, K) same dtype, bias (N,) fp32, residual (..., N).
-    ``impl``: "tc" = the tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``; K % 8 == 0, N a multiple of
-    160 or 256, dense operands), "lib" = library GEMM followed by the fused bias / residual pass, "auto" = ``LINEAR_IMPL``.
+    ``impl``: "tc" = the tcgen05 GEMM with bias / residual in its epilogue (``dadd_linear_fwd``; K % 8 == 0, N % 64 == 0,
+    dense operands), "lib" = library GEMM followed by the fused bias / residual pass, "auto" = ``LINEAR_IMPL``.
     ``bias_lp``: the same bias in x's dtype for the library GEMM's own epilogue (callers keep it in ``wcache``; cast on the
     fly when absent)."""
     _cuda(x, w, bias, residual)

@@ -183,6 +183,12 @@ if on("lin"):
             report(f"{name} library N={N} C={C} B={B}", us, mn, flops=flops)
             us, mn = timeit(lambda: ops.linear(inp, w, b32, r if use_res else None, impl="tc"))
             report(f"{name} tcgen05 N={N} C={C} B={B}", us, mn, flops=flops)
+            if use_res:      # the form the transformer blocks use: no bias (it rides on the stored residual), beta = 1 accumulate
+                yo = torch.empty_like(r)
+                us, mn = timeit(lambda: torch.addmm(r.view(-1, nout), inp.view(-1, kin), w.t(), out=yo.view(-1, nout)))
+                report(f"{name}(no bias) library beta=1 N={N} C={C} B={B}", us, mn, flops=flops)
+                us, mn = timeit(lambda: ops.linear(inp, w, None, r, impl="tc"))
+                report(f"{name}(no bias) tcgen05 N={N} C={C} B={B}", us, mn, flops=flops)
 
 if on("add_ln"):
     for C, N in sites:

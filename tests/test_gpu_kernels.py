@@ -367,7 +367,7 @@ def test_ff_geglu_gemm_vs_fp32(m, k, inner, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
 @pytest.mark.parametrize("m,n,k", [(1024 * 3, 320, 320), (256 * 5, 640, 640), (64 * 7 + 5, 1280, 1280), (16, 1280, 1280),
-                                    (1024 * 40, 960, 320), (2048, 320, 1280), (300, 160, 72), (1664, 3840, 1280), (777, 1920, 640),
+                                    (1024 * 40, 960, 320), (2048, 320, 1280), (300, 192, 72), (500, 64, 136), (1664, 3840, 1280), (777, 1920, 640),
                                     (129, 512, 512)])
 def test_linear_gemm_bias_residual_vs_fp32(m, n, k, dtype):
     """dadd_linear_fwd (both tile widths, ragged M, K not a multiple of 64, many tiles per CTA) with every bias / residual
