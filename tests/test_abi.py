@@ -74,10 +74,12 @@ def test_argument_validation_of_the_newer_entry_points(lib):
     err = lambda: l.dadd_last_error().decode()
     assert l.dadd_linear_supported(1024, 320, 320) == 1 and l.dadd_linear_supported(1024, 96, 320) == 0
     assert l.dadd_linear_supported(1024, 320, 324) == 0                     # K % 8
-    assert l.dadd_linear_fwd(16, 16, None, None, 16, 128, 96, 320, 1, None) != 0 and "multiple of 160 or 256" in err()
+    assert l.dadd_linear_fwd(16, 16, None, None, 16, 128, 96, 320, 1, None) != 0 and "N % 64 == 0" in err()
     assert l.dadd_linear_fwd(None, 16, None, None, 16, 128, 320, 320, 1, None) != 0 and "dadd_linear_fwd" in err()
     assert l.dadd_ff_geglu_fwd(16, 16, 16, 16, 128, 320, 1000, 1, None) != 0 and "inner % 128" in err()
     assert l.dadd_ff_geglu_fwd(16, 16, 16, 16, 128, 320, 1280, 0, None) != 0 and "dtype16_ok" in err()      # fp32 not taken
+    assert l.dadd_self_attn_fwd(16, 16, 16, 600, 600, 600, 16, 200, 1, 1, 64, 200, 0.1, 1, 0, None) != 0 and "wide" in err()   # d = 200
+    assert l.dadd_groupnorm_select(1) == 0 and l.dadd_groupnorm_select(0) == 1
     assert l.dadd_groupnorm_cat_supported(4, 640, 320, 1024, 32, 1) == 1
     assert l.dadd_groupnorm_cat_supported(4, 644, 320, 1024, 32, 1) == 0    # C1 % 8
     assert l.dadd_groupnorm_cat_supported(4, 640, 320, 1024, 32, 0) == 0    # fp32
