@@ -143,7 +143,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CU
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], PAIR ? 512 : 256);         // (PAIR: the leader's is the one in use) both CTAs' epilogue threads
+            mbar_init(&bars->acc_empty[a], PAIR ? 4 : 2);             // one arrival per epilogue warp group (PAIR: of both CTAs, on the leader's barrier)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -253,11 +253,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CU
                     for (int j = 0; j < 8; ++j) rr[j] = rp[j];
                 }
                 tmem_wait_ld();
-                if (c + 2 >= NCH) {                                   // my last read of this accumulator: hand it back to the MMA warp
-                    fence_before();
-                    if (rank == 0) mbar_arrive(&bars->acc_empty[a]);
-                    else mbar_arrive_remote(map_to_rank(smem_u32(&bars->acc_empty[a]), 0));
-                }
+                const bool last_read = c + 2 >= NCH;                  // the group's last read of this accumulator
+                if (last_read) fence_before();
                 const float* bc = bs + c * 64;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -282,6 +279,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CU
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 named_sync(2 + group, 128);
                 if (store_leader) {
+                    if (last_read) {                                  // hand the accumulator back to the MMA warp: ONE (remote) arrival per group
+                        if (rank == 0) mbar_arrive(&bars->acc_empty[a]);
+                        else mbar_arrive_remote(map_to_rank(smem_u32(&bars->acc_empty[a]), 0));
+                    }
                     tma_store_2d(&ty, smem_u32(panel), n0 + c * 64, m0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
