@@ -6,6 +6,7 @@
 //   dadd_minsnr_mse        Min-SNR-weighted MSE loss and its gradient in one pass
 //   dadd_sumsq / dadd_clip_coef / dadd_adamw_step   gradient-norm clipping and AdamW over the flat fp32 buckets of the
 //                          data-parallel trainer (one launch per bucket, no host synchronisation)
+//   dadd_ema_update        EMA weight averaging over the same buckets (the reference's EMAWeightAveraging callback)
 // All reductions are two-stage and atomics-free: results are bit-reproducible run to run.  HBM-bound elementwise / row-wise
 // work: 16-byte accesses, fp32 arithmetic, grids sized in multiples of the SM count.
 #include "common.cuh"
@@ -598,6 +599,40 @@ extern "C" int dadd_clip_coef(const float* partials, int n, float max_norm, floa
     DADD_REQUIRE(partials && coef_and_norm && n > 0, "dadd_clip_coef");
     clip_coef_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, n, max_norm, grad_scale, coef_and_norm);
     return launched("dadd_clip_coef");
+}
+
+// EMA weight averaging over a flat bucket: avg += (p - avg) * (1 - decay)  (torch.optim.swa_utils.get_ema_avg_fn, the avg_fn of the
+// reference's EMAWeightAveraging callback, src/callbacks/ema_callback.py:414-436); first = 1: avg = p (AveragedModel's first update).
+// An overflowed step (coef[0] not finite: the parameters were left untouched) still averages, like the callback does.
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ avg, const float* __restrict__ p, int64_t n, float omd, int first) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 pp = reinterpret_cast<const float4*>(p)[i];
+        float4 aa = reinterpret_cast<float4*>(avg)[i];
+        if (first) {
+            aa = pp;
+        } else {
+            aa.x = fmaf(pp.x - aa.x, omd, aa.x);
+            aa.y = fmaf(pp.y - aa.y, omd, aa.y);
+            aa.z = fmaf(pp.z - aa.z, omd, aa.z);
+            aa.w = fmaf(pp.w - aa.w, omd, aa.w);
+        }
+        reinterpret_cast<float4*>(avg)[i] = aa;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n4 << 2; i < n; ++i) avg[i] = first ? p[i] : fmaf(p[i] - avg[i], omd, avg[i]);
+}
+
+extern "C" int dadd_ema_update(float* avg, const float* p, int64_t n, float decay, int first, void* stream) {
+    DADD_REQUIRE(avg && p && n >= 0, "dadd_ema_update");
+    DADD_REQUIRE(decay >= 0.0f && decay <= 1.0f, "dadd_ema_update");
+    DADD_REQUIRE((((uintptr_t)avg | (uintptr_t)p) % 16) == 0, "dadd_ema_update");
+    if (n == 0) return 0;
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    const int grid = (int)(blocks < 8 * (int64_t)num_sms() ? blocks : 8 * (int64_t)num_sms());
+    ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(avg, p, n, 1.0f - decay, first);
+    return launched("dadd_ema_update");
 }
 
 extern "C" int dadd_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -481,6 +481,13 @@ def clip_coef_(partials: torch.Tensor, max_norm: float, grad_scale: float, coef_
                                           _stream()), "dadd_clip_coef")
 
 
+def ema_update_(avg: torch.Tensor, p: torch.Tensor, decay: float, first: bool = False) -> None:
+    """``avg += (p - avg) * (1 - decay)`` on flat fp32 buffers (``first``: ``avg = p``): torch.optim.swa_utils.get_ema_avg_fn."""
+    _cuda(avg, p)
+    assert avg.dtype == p.dtype == torch.float32 and avg.is_contiguous() and p.is_contiguous() and avg.numel() == p.numel()
+    _lib.check(_lib.load().dadd_ema_update(avg.data_ptr(), p.data_ptr(), p.numel(), float(decay), int(first), _stream()), "dadd_ema_update")
+
+
 def adamw_step_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
                 eps: float, weight_decay: float, step: int, coef: Optional[torch.Tensor] = None) -> None:
     """torch.optim.AdamW's update on flat fp32 buffers, in place; ``g`` is scaled by ``coef[0]`` (device scalar) on the fly."""

@@ -427,8 +427,16 @@ class DataParallelTrainer:
     def __init__(self, module, lr: float = 1e-4, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_grad_norm: float = 1.0, bucket_bytes: int = 64 << 20,
                  param_groups: Optional[List[Dict]] = None, process_group=None, optimizer: str = "fused",
-                 loss_scale: float = 1.0) -> None:
+                 loss_scale: float = 1.0, ema_decay: Optional[float] = None, ema_update_every_n_steps: int = 1,
+                 ema_update_starting_at_step: Optional[int] = None) -> None:
         self.module = module
+        # EMA weight averaging = the reference's EMAWeightAveraging callback (src/callbacks/ema_callback.py:414-472 on Lightning's
+        # WeightAveraging, :168-197; training_pipeline_ip.py:88-92: decay 0.999, from step 100, every 4th step): after optimizer
+        # step number s (1-based) the average is updated when should_update(step_idx = s - 1); the first update copies the
+        # parameters (AveragedModel.n_averaged == 0), later ones are avg += (p - avg) * (1 - decay), one kernel per bucket.
+        self.ema_decay = ema_decay
+        self.ema_every, self.ema_start = int(ema_update_every_n_steps), ema_update_starting_at_step
+        self.ema_updates = 0
         # fp16 compute needs a loss scale (Lightning "16-mixed" runs a GradScaler): the backward pass sees loss * loss_scale, the
         # clip coefficient folds 1 / loss_scale back in, and a step whose scaled gradients overflowed is skipped on the device
         # (``step_overflowed`` reads the flag; halve ``loss_scale`` then).  bf16 (the default compute dtype) runs at 1.
@@ -462,6 +470,9 @@ class DataParallelTrainer:
                 self._bucket_of[id(p)] = (bk, off)
                 p.register_post_accumulate_grad_hook(self._on_grad)
         self.steps = 0
+        if self.ema_decay is not None:       # AveragedModel(pl_module) at setup: a copy of the initial weights (ema_callback.py:135-166)
+            for bk in self.buckets:
+                bk.avg = bk.flat_p.clone()
         dev = self.buckets[0].flat_p.device
         self.coef = torch.ones(2, device=dev, dtype=torch.float32)
         self.partials = torch.zeros(len(self.buckets), ops.SUMSQ_PARTIALS, device=dev, dtype=torch.float32)
@@ -531,6 +542,55 @@ class DataParallelTrainer:
                 denom = (bk.v.sqrt() / math.sqrt(1.0 - b2 ** self.steps)).add_(self.eps)
                 bk.flat_p.addcdiv_(bk.m, denom, value=-lr / (1.0 - b1 ** self.steps))
         wcache.clear()        # inference-time derived weights (16-bit / fused copies) are stale after an in-place update
+        if self.ema_decay is not None and self.ema_should_update(self.steps - 1):
+            self.ema_update()
+
+    # ------------------------------------------------------------------ EMA weight averaging
+    def ema_should_update(self, step_idx: int) -> bool:
+        """EMAWeightAveraging.should_update(step_idx=...) (ema_callback.py:438-472), step conditions only."""
+        meets_start = self.ema_start is None or step_idx >= self.ema_start
+        meets_frequency = self.ema_every > 0 and step_idx % self.ema_every == 0
+        return meets_start and meets_frequency
+
+    def ema_update(self) -> None:
+        first = self.ema_updates == 0
+        for bk in self.buckets:
+            if self.optimizer == "fused":
+                ops.ema_update_(bk.avg, bk.flat_p, self.ema_decay, first)
+            elif first:
+                bk.avg.copy_(bk.flat_p)
+            else:
+                bk.avg.lerp_(bk.flat_p, 1.0 - self.ema_decay)              # torch.optim.swa_utils.get_ema_avg_fn
+        self.ema_updates += 1
+
+    def ema_state_dict(self) -> Dict[str, torch.Tensor]:
+        """The module's state dict with every trained parameter replaced by its average: what the callback writes as
+        ``checkpoint["state_dict"]`` (ema_callback.py:316-323).  Frozen / never-used parameters and buffers are constants of the
+        run, so their average is their value.  Before the first update the average model holds the initial weights (:135-166)."""
+        assert self.ema_decay is not None, "the trainer was built without ema_decay"
+        sd = {k: v.detach().clone() for k, v in self.module.state_dict().items()}
+        names = {id(p): n for n, p in self.module.named_parameters()}
+        for bk in self.buckets:
+            for p, off in zip(bk.params, bk.offsets):
+                sd[names[id(p)]] = bk.avg[off:off + p.numel()].view_as(p).clone()
+        return sd
+
+    def swap_ema_weights(self) -> None:
+        """Exchange the parameters with their averages in place (the callback's ``_swap_models`` around validation,
+        ema_callback.py:235-265,379-395); call again to swap back."""
+        assert self.ema_decay is not None, "the trainer was built without ema_decay"
+        for bk in self.buckets:
+            tmp = bk.flat_p.clone()
+            bk.flat_p.copy_(bk.avg)
+            bk.avg.copy_(tmp)
+        wcache.clear()
+
+    def copy_ema_to_model(self) -> None:
+        """End of training: the module takes the averaged weights (``_copy_average_to_current``, ema_callback.py:219-233,397-411)."""
+        assert self.ema_decay is not None, "the trainer was built without ema_decay"
+        for bk in self.buckets:
+            bk.flat_p.copy_(bk.avg)
+        wcache.clear()
 
     def set_epoch_lr(self, epoch: int, warmup_epochs: int, max_epochs: int, min_lr: float) -> None:
         """Per-epoch LinearWarmupCosineAnnealingLR (diffusion_module_ip.py:521-527), applied as a scale on every group's lr."""

@@ -178,6 +178,23 @@ def setup():
     return module, state
 
 
+def test_ema_update_kernel_matches_torch_ema_avg_fn():
+    """dadd_ema_update on a flat bucket vs torch.optim.swa_utils.get_ema_avg_fn (the avg_fn of the reference's EMAWeightAveraging,
+    src/callbacks/ema_callback.py:414-436); odd length (scalar tail), first-update copy, and the trainer driving it on the
+    callback's schedule."""
+    from torch.optim.swa_utils import get_ema_avg_fn
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    n = 4 * 100003 + 3
+    avg, p = torch.randn(n, generator=g).to(DEV), torch.randn(n, generator=g).to(DEV)
+    want = get_ema_avg_fn(0.999)(avg.clone(), p, 7)
+    got = avg.clone()
+    ops.ema_update_(got, p, 0.999)
+    torch.testing.assert_close(got, want, rtol=0, atol=1e-7)
+    ops.ema_update_(got, p, 0.999, first=True)
+    assert torch.equal(got, p)
+
+
 def test_vae_encoder_matches_oracle(setup):
     module, state = setup
     vw = weights.sub_state(state, "vae.vae.")
@@ -278,9 +295,20 @@ def test_training_loss_end_to_end_and_optimizer_steps(setup):
     assert aux["cfg_drop_rate"].item() == 0.5
 
     keep = {n: dict(module.named_parameters())[n].detach().clone() for n in T.UNUSED_PARAMETERS}
-    trainer = T.DataParallelTrainer(module, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0)
+    probe = "unet.unet.conv_in.weight"
+    trainer = T.DataParallelTrainer(module, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, ema_decay=0.9, ema_update_every_n_steps=1,
+                                    ema_update_starting_at_step=1)
     assert sorted(trainer.unused) == sorted(T.UNUSED_PARAMETERS)
-    losses = [trainer.step(lambda: T.training_loss(module, lat.to(DEV), labels.to(DEV), tok.to(DEV), **kw)[0]).item() for _ in range(3)]
+    w0 = dict(module.named_parameters())[probe].detach().clone()
+    assert torch.equal(trainer.ema_state_dict()[probe], w0)               # the average model starts as a copy of the module
+    losses, seen = [], []
+    for _ in range(3):
+        losses.append(trainer.step(lambda: T.training_loss(module, lat.to(DEV), labels.to(DEV), tok.to(DEV), **kw)[0]).item())
+        seen.append(dict(module.named_parameters())[probe].detach().clone())
+    # EMA on the reference callback's schedule (from step index 1, every step): first update copies, second lerps
+    want_avg = seen[1] + (seen[2] - seen[1]) * (1 - 0.9)
+    torch.testing.assert_close(trainer.ema_state_dict()[probe], want_avg, rtol=0, atol=1e-7)
+    assert trainer.ema_updates == 2
     print("losses over 3 steps:", losses, "grad norm", trainer.grad_norm.item())
     assert losses[0] == pytest.approx(want, rel=2e-2) and losses[2] < losses[0] and all(math.isfinite(v) for v in losses)
     for n, v in keep.items():

@@ -101,6 +101,42 @@ def test_trainer_matches_torch_adamw_and_detects_missing_gradients():
         tr.step(lambda: (m.unet(x) ** 2).mean())                          # purifier / projection / AOE left out of the loss
 
 
+def test_ema_weight_averaging_follows_the_reference_callback():
+    """DataParallelTrainer's EMA against torch.optim.swa_utils.AveragedModel + get_ema_avg_fn - the machinery Lightning's
+    WeightAveraging drives in the reference (src/callbacks/ema_callback.py:135-197,414-472) - on the callback's schedule:
+    update after optimizer step s when (s - 1) >= update_starting_at_step and (s - 1) % update_every_n_steps == 0."""
+    from torch.optim.swa_utils import AveragedModel, get_ema_avg_fn
+    torch.manual_seed(1)
+    m = _Tiny()
+    decay, every, start = 0.9, 2, 1
+    tr = T.DataParallelTrainer(m, lr=1e-2, weight_decay=0.05, max_grad_norm=0.5, optimizer="torch", bucket_bytes=64,
+                               ema_decay=decay, ema_update_every_n_steps=every, ema_update_starting_at_step=start)
+    avg = AveragedModel(m, avg_fn=get_ema_avg_fn(decay), use_buffers=True)
+    x, y = torch.randn(16, 6), torch.randn(16, 4)
+    updates = 0
+    for s in range(1, 9):
+        tr.step(lambda: ((m(x) - y) ** 2).mean())
+        step_idx = s - 1
+        if step_idx >= start and step_idx % every == 0:                   # EMAWeightAveraging.should_update
+            avg.update_parameters(m)
+            updates += 1
+        assert tr.ema_updates == updates
+        ema = tr.ema_state_dict()
+        for n, v in avg.module.state_dict().items():
+            torch.testing.assert_close(ema[n], v, rtol=1e-6, atol=1e-7, msg=f"step {s}: {n}")
+    assert updates == 3
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    tr.swap_ema_weights()                                                 # validation runs on the averaged weights ...
+    for n, p in m.named_parameters():
+        torch.testing.assert_close(p, avg.module.state_dict()[n], rtol=1e-6, atol=1e-7, msg=n)
+    tr.swap_ema_weights()                                                 # ... and training continues on the current ones
+    for n, p in m.named_parameters():
+        assert torch.equal(p, before[n]), n
+    tr.copy_ema_to_model()                                                # end of fit
+    for n, p in m.named_parameters():
+        torch.testing.assert_close(p, avg.module.state_dict()[n], rtol=1e-6, atol=1e-7, msg=n)
+
+
 def test_conditioning_train_functions_match_oracle():
     """aoe_train / purifier_train are the autograd twins of the inference kernels: same numbers as the (reference-pinned) oracle."""
     from progressive_stable_diffusion_b200.feature_purifier import FeaturePurifier
