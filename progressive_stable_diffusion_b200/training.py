@@ -437,6 +437,7 @@ class DataParallelTrainer:
         self.ema_decay = ema_decay
         self.ema_every, self.ema_start = int(ema_update_every_n_steps), ema_update_starting_at_step
         self.ema_updates = 0
+        self._ema_latest_step = 0
         # fp16 compute needs a loss scale (Lightning "16-mixed" runs a GradScaler): the backward pass sees loss * loss_scale, the
         # clip coefficient folds 1 / loss_scale back in, and a step whose scaled gradients overflowed is skipped on the device
         # (``step_overflowed`` reads the flag; halve ``loss_scale`` then).  bf16 (the default compute dtype) runs at 1.
@@ -562,6 +563,7 @@ class DataParallelTrainer:
             else:
                 bk.avg.lerp_(bk.flat_p, 1.0 - self.ema_decay)              # torch.optim.swa_utils.get_ema_avg_fn
         self.ema_updates += 1
+        self._ema_latest_step = self.steps
 
     def ema_state_dict(self) -> Dict[str, torch.Tensor]:
         """The module's state dict with every trained parameter replaced by its average: what the callback writes as
@@ -590,6 +592,39 @@ class DataParallelTrainer:
         assert self.ema_decay is not None, "the trainer was built without ema_decay"
         for bk in self.buckets:
             bk.flat_p.copy_(bk.avg)
+        wcache.clear()
+
+    # ------------------------------------------------------------------ checkpoints in the reference's layout
+    def checkpoint(self, epoch: int = 0) -> Dict:
+        """The dictionary Lightning + the EMA callback write (ema_callback.py:291-330): ``state_dict`` = averaged weights (what
+        ``load_from_checkpoint`` and the inference / evaluation pipelines read), ``current_model_state`` = the weights training
+        continues from, ``averaging_state`` = AveragedModel's own entries (``n_averaged``), the callback's ``latest_update_step``
+        and the optimizer moments per bucket.  Without EMA: ``state_dict`` = the current weights."""
+        cur = {k: v.detach().clone() for k, v in self.module.state_dict().items()}
+        ck = {"epoch": int(epoch), "global_step": int(self.steps), "state_dict": cur,
+              "optimizer_moments": [None if bk.m is None else (bk.m.clone(), bk.v.clone()) for bk in self.buckets]}
+        if self.ema_decay is not None:
+            ck["state_dict"] = self.ema_state_dict()
+            ck["current_model_state"] = cur
+            ck["averaging_state"] = {"n_averaged": torch.tensor(self.ema_updates, dtype=torch.long)}
+            ck["callbacks"] = {"EMAWeightAveraging": {"latest_update_step": int(self._ema_latest_step)}}
+        return ck
+
+    def load_checkpoint(self, ck: Dict) -> None:
+        """Resume: the module takes ``current_model_state`` and the averages come from ``state_dict`` (on_load_checkpoint,
+        ema_callback.py:332-378); a checkpoint written without EMA initialises both from ``state_dict``."""
+        names = {id(p): n for n, p in self.module.named_parameters()}
+        self.module.load_state_dict(ck.get("current_model_state", ck["state_dict"]), strict=False)     # copies into the bucket views
+        self.steps = int(ck.get("global_step", 0))
+        if self.ema_decay is not None:
+            for bk in self.buckets:
+                for p, off in zip(bk.params, bk.offsets):
+                    bk.avg[off:off + p.numel()].copy_(ck["state_dict"][names[id(p)]].reshape(-1))
+            self.ema_updates = int(ck["averaging_state"]["n_averaged"]) if "averaging_state" in ck else 0
+            self._ema_latest_step = int(ck.get("callbacks", {}).get("EMAWeightAveraging", {}).get("latest_update_step", 0))
+        for bk, mom in zip(self.buckets, ck.get("optimizer_moments", [])):
+            if mom is not None:
+                bk.m, bk.v = mom[0].to(bk.flat_p.device).clone(), mom[1].to(bk.flat_p.device).clone()
         wcache.clear()
 
     def set_epoch_lr(self, epoch: int, warmup_epochs: int, max_epochs: int, min_lr: float) -> None:

@@ -137,6 +137,42 @@ def test_ema_weight_averaging_follows_the_reference_callback():
         torch.testing.assert_close(p, avg.module.state_dict()[n], rtol=1e-6, atol=1e-7, msg=n)
 
 
+def test_checkpoint_layout_and_resume(tmp_path):
+    """The trainer writes the reference's checkpoint layout (ema_callback.py:291-330: averaged weights under ``state_dict``, the
+    training weights under ``current_model_state``) and a resumed trainer continues bit for bit."""
+    torch.manual_seed(2)
+    x, y = torch.randn(16, 6), torch.randn(16, 4)
+    kw = dict(lr=1e-2, weight_decay=0.05, max_grad_norm=0.5, optimizer="torch", bucket_bytes=64, ema_decay=0.9,
+              ema_update_every_n_steps=1, ema_update_starting_at_step=0)
+    m = _Tiny()
+    tr = T.DataParallelTrainer(m, **kw)
+    for _ in range(3):
+        tr.step(lambda: ((m(x) - y) ** 2).mean())
+    path = tmp_path / "last.ckpt"
+    torch.save(tr.checkpoint(epoch=1), path)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) >= {"state_dict", "current_model_state", "averaging_state", "global_step", "epoch"}
+    assert ck["global_step"] == 3 and int(ck["averaging_state"]["n_averaged"]) == 3
+    assert set(ck["state_dict"]) == set(m.state_dict())
+    ema = tr.ema_state_dict()
+    assert all(torch.equal(ck["state_dict"][k], ema[k]) for k in ema)
+    assert any(not torch.equal(ck["state_dict"][k], ck["current_model_state"][k]) for k in ema)
+    # an inference-side loader reads state_dict (= averaged weights): the module API takes it as is
+    m_inf = _Tiny()
+    m_inf.load_state_dict(ck["state_dict"], strict=True)
+    # resume: same next step as the uninterrupted run
+    m2 = _Tiny()
+    tr2 = T.DataParallelTrainer(m2, **kw)
+    tr2.load_checkpoint(ck)
+    l1 = tr.step(lambda: ((m(x) - y) ** 2).mean())
+    l2 = tr2.step(lambda: ((m2(x) - y) ** 2).mean())
+    assert torch.equal(l1, l2)
+    for (n, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p, q), n
+    e1, e2 = tr.ema_state_dict(), tr2.ema_state_dict()
+    assert all(torch.equal(e1[k], e2[k]) for k in e1)
+
+
 def test_conditioning_train_functions_match_oracle():
     """aoe_train / purifier_train are the autograd twins of the inference kernels: same numbers as the (reference-pinned) oracle."""
     from progressive_stable_diffusion_b200.feature_purifier import FeaturePurifier
