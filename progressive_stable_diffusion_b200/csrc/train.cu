@@ -631,7 +631,7 @@ extern "C" int dadd_ema_update(float* avg, const float* p, int64_t n, float deca
     int64_t blocks = ((n >> 2) + 255) / 256;
     if (blocks < 1) blocks = 1;
     const int grid = (int)(blocks < 8 * (int64_t)num_sms() ? blocks : 8 * (int64_t)num_sms());
-    ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(avg, p, n, 1.0f - decay, first);
+    ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(avg, p, n, (float)(1.0 - (double)decay), first);
     return launched("dadd_ema_update");
 }
 

@@ -190,7 +190,7 @@ def test_ema_update_kernel_matches_torch_ema_avg_fn():
     want = get_ema_avg_fn(0.999)(avg.clone(), p, 7)
     got = avg.clone()
     ops.ema_update_(got, p, 0.999)
-    torch.testing.assert_close(got, want, rtol=0, atol=1e-7)
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)      # (fused multiply-add vs torch's separate multiply and add)
     ops.ema_update_(got, p, 0.999, first=True)
     assert torch.equal(got, p)
 
@@ -307,7 +307,7 @@ def test_training_loss_end_to_end_and_optimizer_steps(setup):
         seen.append(dict(module.named_parameters())[probe].detach().clone())
     # EMA on the reference callback's schedule (from step index 1, every step): first update copies, second lerps
     want_avg = seen[1] + (seen[2] - seen[1]) * (1 - 0.9)
-    torch.testing.assert_close(trainer.ema_state_dict()[probe], want_avg, rtol=0, atol=1e-7)
+    torch.testing.assert_close(trainer.ema_state_dict()[probe], want_avg, rtol=1e-6, atol=1e-6)
     assert trainer.ema_updates == 2
     print("losses over 3 steps:", losses, "grad norm", trainer.grad_norm.item())
     assert losses[0] == pytest.approx(want, rel=2e-2) and losses[2] < losses[0] and all(math.isfinite(v) for v in losses)
