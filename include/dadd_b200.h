@@ -30,7 +30,7 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change).  The host binding refuses a library whose
  * dadd_abi_version() differs from the DADD_ABI_VERSION it was written against. */
-#define DADD_ABI_VERSION 12
+#define DADD_ABI_VERSION 13
 int dadd_abi_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* dadd_last_error(void);
@@ -263,6 +263,11 @@ int dadd_sumsq(const float* g, int64_t n, float* partials, int n_partials, void*
 int dadd_clip_coef(const float* partials, int n, float max_norm, float grad_scale, float* coef_and_norm, void* stream);
 int dadd_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, float bias_corr1, float bias_corr2, const float* coef, void* stream);
+/* The same update with the step-dependent scalars on the device: dev_state[0] scales lr (the schedule), dev_state[1] is the step
+ * number t of the bias corrections 1 - beta^t.  Lets ONE captured CUDA graph of the whole training step (forward, backward,
+ * gradient all-reduce, clip, AdamW) replay for every step: nothing the host passes changes between replays. */
+int dadd_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, const float* dev_state /* {lr scale, step} */, const float* coef, void* stream);
 /* EMA weight averaging of a flat fp32 parameter bucket: avg += (p - avg) * (1 - decay); first != 0: avg = p.  Replaces the
  * AveragedModel.update_parameters call of the reference's EMAWeightAveraging callback (src/callbacks/ema_callback.py:168-197,414-436:
  * torch.optim.swa_utils.get_ema_avg_fn(decay), decay 0.999, every 4th step from step 100 in configs/train_ip.yaml:83-85). */

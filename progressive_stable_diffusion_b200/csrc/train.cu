@@ -444,11 +444,20 @@ __global__ void clip_coef_kernel(const float* __restrict__ part, int n, float ma
     }
 }
 // torch.optim.AdamW semantics (decoupled decay first, then the moment update); g is scaled by *coef on the fly
+// dev_state != nullptr: {learning-rate scale, step number} live on the device (bc1 / bc2 ignored): a captured CUDA graph of the
+// whole training step replays with the right bias corrections and schedule without any host-side argument changing
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                                    float wd, float bc1, float bc2, const float* __restrict__ coef) {
+                                                    float wd, float bc1, float bc2, const float* __restrict__ coef,
+                                                    const float* __restrict__ dev_state) {
     const float c = coef ? coef[0] : 1.0f;
     if (!isfinite(c)) return;                                    // overflowed step: leave parameters and moments untouched
+    if (dev_state) {
+        lr *= dev_state[0];
+        const float t = dev_state[1];
+        bc1 = 1.0f - powf(b1, t);
+        bc2 = 1.0f - powf(b2, t);
+    }
     const float step = lr / bc1, rbc2 = rsqrtf(bc2);
     const int64_t n4 = n >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -643,8 +652,20 @@ extern "C" int dadd_adamw_step(float* p, const float* g, float* m, float* v, int
     int64_t blocks = ((n >> 2) + 255) / 256;
     if (blocks < 1) blocks = 1;
     const int grid = (int)(blocks < 8 * (int64_t)num_sms() ? blocks : 8 * (int64_t)num_sms());
-    adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, coef);
+    adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, coef, nullptr);
     return launched("dadd_adamw_step");
+}
+
+extern "C" int dadd_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                   float weight_decay, const float* dev_state, const float* coef, void* stream) {
+    DADD_REQUIRE(p && g && m && v && dev_state && n >= 0, "dadd_adamw_step_dev");
+    DADD_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0, "dadd_adamw_step_dev");
+    if (n == 0) return 0;
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    const int grid = (int)(blocks < 8 * (int64_t)num_sms() ? blocks : 8 * (int64_t)num_sms());
+    adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f, 1.0f, coef, dev_state);
+    return launched("dadd_adamw_step_dev");
 }
 
 // ------------------------------------------------------------------------------------------------ cross-attention backward

@@ -481,6 +481,18 @@ def clip_coef_(partials: torch.Tensor, max_norm: float, grad_scale: float, coef_
                                           _stream()), "dadd_clip_coef")
 
 
+def adamw_step_dev_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
+                    eps: float, weight_decay: float, dev_state: torch.Tensor, coef: Optional[torch.Tensor] = None) -> None:
+    """``adamw_step_`` with the learning-rate scale and the step number read from ``dev_state`` = [scale, step] on the device
+    (graph-capturable: no host-side argument depends on the step)."""
+    _cuda(p, g, m, v, dev_state, coef)
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    assert dev_state.dtype == torch.float32 and dev_state.numel() >= 2
+    _lib.check(_lib.load().dadd_adamw_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                                               weight_decay, dev_state.data_ptr(), _ptr(coef), _stream()), "dadd_adamw_step_dev")
+
+
 def ema_update_(avg: torch.Tensor, p: torch.Tensor, decay: float, first: bool = False) -> None:
     """``avg += (p - avg) * (1 - decay)`` on flat fp32 buffers (``first``: ``avg = p``): torch.optim.swa_utils.get_ema_avg_fn."""
     _cuda(avg, p)

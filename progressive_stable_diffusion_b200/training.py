@@ -314,7 +314,7 @@ def min_snr_weight(module, t: torch.Tensor) -> torch.Tensor:
     if not module.cfg.training.use_min_snr_weighting:
         return torch.ones_like(t, dtype=torch.float32)
     snr = module.snr_values.to(t.device)[t]
-    return torch.minimum(snr, torch.tensor(module.diff_cfg.min_snr_gamma, device=snr.device)) / (snr + 1e-8)
+    return torch.clamp(snr, max=float(module.diff_cfg.min_snr_gamma)) / (snr + 1e-8)      # min(snr, gamma), no host tensor (graph capture)
 
 
 class _MinSnrMse(torch.autograd.Function):
@@ -478,6 +478,10 @@ class DataParallelTrainer:
         self.coef = torch.ones(2, device=dev, dtype=torch.float32)
         self.partials = torch.zeros(len(self.buckets), ops.SUMSQ_PARTIALS, device=dev, dtype=torch.float32)
         self.lr_scale = 1.0
+        # {lr scale, step number} as the fused AdamW reads them: on the device, advanced in stream order, so that a captured graph
+        # of the whole step (``capture``) replays with the right schedule and bias corrections
+        self.dev_state = torch.tensor([1.0, 0.0], device=dev, dtype=torch.float32) if dev.type == "cuda" else None
+        self._graph = None
 
     # ------------------------------------------------------------------ backward-time hooks
     def _on_grad(self, p: nn.Parameter) -> None:
@@ -520,14 +524,15 @@ class DataParallelTrainer:
         b1, b2 = self.betas
         inv_world = 1.0 / (self.world * self.loss_scale)
         if self.optimizer == "fused":
+            self.dev_state[1:2].add_(1.0)                                   # the step number, in stream order (captured with the step)
             for i, bk in enumerate(self.buckets):
                 ops.sumsq_(bk.flat_g, self.partials[i])
             ops.clip_coef_(self.partials.view(-1), self.max_grad_norm, inv_world, self.coef)
             for bk in self.buckets:
                 if bk.m is None:
                     bk.m, bk.v = torch.zeros_like(bk.flat_p), torch.zeros_like(bk.flat_p)
-                ops.adamw_step_(bk.flat_p, bk.flat_g, bk.m, bk.v, bk.lr * self.lr_scale, b1, b2, self.eps, self.weight_decay,
-                                self.steps, self.coef)
+                ops.adamw_step_dev_(bk.flat_p, bk.flat_g, bk.m, bk.v, bk.lr, b1, b2, self.eps, self.weight_decay, self.dev_state,
+                                    self.coef)
         else:       # reference arithmetic with stock PyTorch (CPU / gloo tests of the bucket logic)
             total = torch.sqrt(sum((bk.flat_g * inv_world).pow(2).sum() for bk in self.buckets))
             coef = inv_world * (torch.clamp(self.max_grad_norm / (total + 1e-6), max=1.0) if self.max_grad_norm > 0 else 1.0)
@@ -616,6 +621,8 @@ class DataParallelTrainer:
         names = {id(p): n for n, p in self.module.named_parameters()}
         self.module.load_state_dict(ck.get("current_model_state", ck["state_dict"]), strict=False)     # copies into the bucket views
         self.steps = int(ck.get("global_step", 0))
+        if self.dev_state is not None:
+            self.dev_state[1:2].fill_(float(self.steps))
         if self.ema_decay is not None:
             for bk in self.buckets:
                 for p, off in zip(bk.params, bk.offsets):
@@ -631,6 +638,8 @@ class DataParallelTrainer:
         """Per-epoch LinearWarmupCosineAnnealingLR (diffusion_module_ip.py:521-527), applied as a scale on every group's lr."""
         lr = warmup_cosine_lr(epoch, self.base_lr, warmup_epochs, max_epochs, self.base_lr * 0.01, min_lr)
         self.lr_scale = lr / self.base_lr
+        if self.dev_state is not None:
+            self.dev_state[0:1].fill_(self.lr_scale)
 
     def step(self, loss_fn) -> torch.Tensor:
         self.zero_grad()
@@ -639,6 +648,50 @@ class DataParallelTrainer:
         self.finish_reduce()
         self.optimizer_step()
         return loss.detach()
+
+    def capture(self, loss_fn, generators=(), warmup: int = 2):
+        """Capture ONE CUDA graph of the whole step - gradient-bucket zeroing, forward, backward with the bucket all-reduces launched
+        from the gradient hooks, clip, AdamW - and return ``replay() -> loss``.  At batch 8 per GPU the eager step is bound by the
+        host (5 700 launches behind Python autograd; the kernels add up to half of its wall time); a replay is one launch.
+        ``loss_fn`` must read its inputs from tensors that keep their address (copy each batch into them before ``replay()``) and
+        draw its random numbers from the default CUDA generator or from ``generators`` (registered with the graph).  ``warmup``
+        eager steps run first (they are real optimizer steps): cuDNN / cuBLAS plans, the allocator, NCCL.  The step number and the
+        learning-rate scale live on the device (``dadd_adamw_step_dev``); EMA updates are issued by ``replay`` on the reference
+        callback's schedule.  All ranks must capture and replay together (NCCL is captured)."""
+        assert self.optimizer == "fused" and self.dev_state is not None, "graph capture needs the fused CUDA optimizer"
+        dev = self.buckets[0].flat_p.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(loss_fn)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for bk in self.buckets:                      # (moments exist before the capture: no allocation inside the graph's optimizer)
+            if bk.m is None:
+                bk.m, bk.v = torch.zeros_like(bk.flat_p), torch.zeros_like(bk.flat_p)
+        graph = torch.cuda.CUDAGraph()
+        for gen in generators:
+            graph.register_generator_state(gen)
+        ema_decay, self.ema_decay = self.ema_decay, None      # the host-side EMA decision stays out of the captured step
+        steps_before = self.steps
+        try:
+            with torch.cuda.graph(graph):
+                loss = self.step(loss_fn)
+        finally:
+            self.ema_decay = ema_decay
+            self.steps = steps_before                 # capturing executes nothing: the step is counted when it is replayed
+        self._graph, self._graph_loss = graph, loss
+
+        def replay() -> torch.Tensor:
+            graph.replay()
+            self.steps += 1
+            wcache.clear()
+            if self.ema_decay is not None and self.ema_should_update(self.steps - 1):
+                self.ema_update()
+            return self._graph_loss
+
+        return replay
 
     @property
     def grad_norm(self) -> torch.Tensor:

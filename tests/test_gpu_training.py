@@ -317,3 +317,43 @@ def test_training_loss_end_to_end_and_optimizer_steps(setup):
     from progressive_stable_diffusion_b200.inference_pipeline_ip import _ddim_sample_ip
     out = _ddim_sample_ip(module, torch.tensor([0.0, 3.0]), torch.zeros(2), tok.to(DEV), 2, DEV, steer_scale=3.0)
     assert torch.isfinite(out).all()
+
+
+def test_graphed_training_step_equals_eager(setup):
+    """DataParallelTrainer.capture: one CUDA graph of bucket zeroing + forward + backward + clip + AdamW (step number and learning-
+    rate scale on the device) against the eager step on a copy of the module, same injected noise / timesteps / drop mask."""
+    import progressive_stable_diffusion_b200 as P
+    from progressive_stable_diffusion_b200 import training as T
+    _, state = setup
+
+    def fresh():
+        m = P.DiffusionModuleWithIP(P.default_config(), build_vae_encoder=True)
+        m.load_state_dict(state, strict=True)
+        return m.to(DEV).eval()
+
+    g = torch.Generator().manual_seed(33)
+    b = 2
+    lat, noise = (torch.randn(b, 4, 32, 32, generator=g) * 0.18215 * 4).to(DEV), torch.randn(b, 4, 32, 32, generator=g).to(DEV)
+    labels, t = torch.tensor([0.5, 3.0], device=DEV), torch.tensor([700, 60], device=DEV)
+    tok = torch.randn(b, 16, 768, generator=g).to(DEV)
+    kw = dict(noise=noise, timesteps=t, aoe_noise_std=0.0, drop_mask=torch.tensor([False, False], device=DEV), compute_dtype=torch.bfloat16)
+    ma, mb = fresh(), fresh()
+    init = {n: p.detach().clone() for n, p in ma.named_parameters()}
+    ta = T.DataParallelTrainer(ma, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, ema_decay=0.9, ema_update_starting_at_step=2)
+    tb = T.DataParallelTrainer(mb, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, ema_decay=0.9, ema_update_starting_at_step=2)
+    la = [ta.step(lambda: T.training_loss(ma, lat, labels, tok, **kw)[0]).item() for _ in range(5)]
+    replay = tb.capture(lambda: T.training_loss(mb, lat, labels, tok, **kw)[0], warmup=2)
+    assert tb.steps == 2
+    lb = [replay().item() for _ in range(3)]
+    print("eager", la, "graphed (after 2 eager warm-up steps)", lb)
+    assert tb.steps == 5 and tb.dev_state[1].item() == 5.0 and tb.ema_updates == ta.ema_updates == 3
+    for x, y in zip(la[2:], lb):
+        assert y == pytest.approx(x, rel=5e-3), (la, lb)
+    assert lb[-1] < la[0]
+    pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
+    for n in ("unet.unet.conv_in.weight", "unet.unet.mid_block.attentions.0.transformer_blocks.0.attn2.to_q.weight", "feature_purifier.gate.0.weight"):
+        ua, ub = (pa[n] - init[n]).flatten().double(), (pb[n] - init[n]).flatten().double()      # what five steps did to the tensor
+        cos = (ua @ ub / (ua.norm() * ub.norm())).item()
+        assert cos >= 0.99, (n, cos)          # (Adam's normalised update flips sign on elements whose bf16 gradient is noise)
+    ea, eb = ta.ema_state_dict(), tb.ema_state_dict()
+    torch.testing.assert_close(ea["unet.unet.conv_in.weight"], eb["unet.unet.conv_in.weight"], rtol=0, atol=1e-4)
