@@ -464,12 +464,18 @@ def run_b200(args) -> None:
         if why:
             extras["config3"]["cuda_graph_error"] = why
         if world > 1:           # exposed share of the gradient all-reduce: the same step with the collective switched off
-            trainer.world = 1
-            step_train()
-            sec_off = timed(step_train, 3)                                   # (eager: compare with ms_per_step_eager)
-            trainer.world = world
+            if graphed:
+                trainer._skip_allreduce = True
+                replay()
+                sec_off = timed(replay, 3)
+                trainer._skip_allreduce = False
+            else:
+                trainer.world = 1
+                step_train()
+                sec_off = timed(step_train, 3)
+                trainer.world = world
             extras["config3"]["ms_per_step_without_allreduce"] = sec_off / 3 * 1e3
-            extras["config3"]["allreduce_exposed_share"] = max(0.0, 1.0 - sec_off / sec_eager)
+            extras["config3"]["allreduce_exposed_share"] = max(0.0, 1.0 - sec_off / sec)
         del trainer
 
     images_total = batch * world * args.steps

@@ -482,6 +482,8 @@ class DataParallelTrainer:
         # of the whole step (``capture``) replays with the right schedule and bias corrections
         self.dev_state = torch.tensor([1.0, 0.0], device=dev, dtype=torch.float32) if dev.type == "cuda" else None
         self._graph = None
+        self._reduce_after_backward = False      # capture() with world > 1: the graph holds forward + backward, the all-reduces follow it
+        self._skip_allreduce = False             # measurement aid (bench: exposed share of the collective)
 
     # ------------------------------------------------------------------ backward-time hooks
     def _on_grad(self, p: nn.Parameter) -> None:
@@ -492,7 +494,7 @@ class DataParallelTrainer:
             slot.copy_(p.grad.reshape(slot.shape))
             p.grad = slot
         bk.pending -= 1
-        if bk.pending == 0 and self.world > 1:
+        if bk.pending == 0 and self.world > 1 and not self._reduce_after_backward:
             bk.work = dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     def zero_grad(self) -> None:
@@ -650,14 +652,18 @@ class DataParallelTrainer:
         return loss.detach()
 
     def capture(self, loss_fn, generators=(), warmup: int = 2):
-        """Capture ONE CUDA graph of the whole step - gradient-bucket zeroing, forward, backward with the bucket all-reduces launched
-        from the gradient hooks, clip, AdamW - and return ``replay() -> loss``.  At batch 8 per GPU the eager step is bound by the
-        host (5 700 launches behind Python autograd; the kernels add up to half of its wall time); a replay is one launch.
+        """Capture the step as a CUDA graph and return ``replay() -> loss``.  At batch 8 per GPU the eager step is bound by the host
+        (5 700 launches behind Python autograd; the kernels add up to half of its wall time); a replay is one launch.
+          * one process (world size 1): ONE graph holds gradient-bucket zeroing, forward, backward, clip and AdamW;
+          * data parallel: the graph holds zeroing + forward + backward; ``replay`` then all-reduces the buckets (NCCL, eager: a
+            capture that includes the hook-launched all-reduces deadlocked against ProcessGroupNCCL's watchdog on this stack,
+            torch 2.11 / NCCL 2.28) and runs the fused clip + AdamW kernels.  The collective is no longer hidden under backward,
+            but the step is still shorter than the host-bound eager one (bench ``config3``).
         ``loss_fn`` must read its inputs from tensors that keep their address (copy each batch into them before ``replay()``) and
         draw its random numbers from the default CUDA generator or from ``generators`` (registered with the graph).  ``warmup``
         eager steps run first (they are real optimizer steps): cuDNN / cuBLAS plans, the allocator, NCCL.  The step number and the
         learning-rate scale live on the device (``dadd_adamw_step_dev``); EMA updates are issued by ``replay`` on the reference
-        callback's schedule.  All ranks must capture and replay together (NCCL is captured)."""
+        callback's schedule.  All ranks must capture and replay together."""
         assert self.optimizer == "fused" and self.dev_state is not None, "graph capture needs the fused CUDA optimizer"
         dev = self.buckets[0].flat_p.device
         side = torch.cuda.Stream(device=dev)
@@ -673,11 +679,22 @@ class DataParallelTrainer:
         graph = torch.cuda.CUDAGraph()
         for gen in generators:
             graph.register_generator_state(gen)
+        whole = self.world == 1
         ema_decay, self.ema_decay = self.ema_decay, None      # the host-side EMA decision stays out of the captured step
         steps_before = self.steps
+        self._reduce_after_backward = not whole
+        if not whole:                                 # no collective in flight while capturing (ProcessGroupNCCL's watchdog polls events)
+            dist.barrier(group=self.pg)
+            torch.cuda.synchronize(dev)
         try:
-            with torch.cuda.graph(graph):
-                loss = self.step(loss_fn)
+            with torch.cuda.graph(graph, capture_error_mode="global" if whole else "thread_local"):
+                if whole:
+                    loss = self.step(loss_fn)
+                else:
+                    self.zero_grad()
+                    loss = loss_fn()
+                    (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
+                    loss = loss.detach()
         finally:
             self.ema_decay = ema_decay
             self.steps = steps_before                 # capturing executes nothing: the step is counted when it is replayed
@@ -685,10 +702,17 @@ class DataParallelTrainer:
 
         def replay() -> torch.Tensor:
             graph.replay()
-            self.steps += 1
-            wcache.clear()
-            if self.ema_decay is not None and self.ema_should_update(self.steps - 1):
-                self.ema_update()
+            if whole:
+                self.steps += 1
+                wcache.clear()
+                if self.ema_decay is not None and self.ema_should_update(self.steps - 1):
+                    self.ema_update()
+            else:
+                if not self._skip_allreduce:
+                    works = [dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for bk in self.buckets]
+                    for w in works:
+                        w.wait()
+                self.optimizer_step()                 # (eager: ~90 launches; counts the step, clears caches, EMA)
             return self._graph_loss
 
         return replay
