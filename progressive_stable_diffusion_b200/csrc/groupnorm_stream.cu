@@ -88,11 +88,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                  ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -184,7 +179,6 @@ gn_stream_kernel(const __grid_constant__ CUtensorMap m1, const __grid_constant__
     const int n_my = (p.items - (int)blockIdx.x + grid - 1) / grid;
     const T* x1 = static_cast<const T*>(p.x);
     const T* x2 = static_cast<const T*>(p.x2);
-    T* y = static_cast<T*>(p.y);
     auto stage_ptr = [&](int st) { return ring + (size_t)st * p.stage_bytes; };
     auto aux_px0 = [&](int st) { return reinterpret_cast<const T*>(stage_ptr(st) + p.aux_off); };
     auto aux_add = [&](int st) { return reinterpret_cast<const float*>(stage_ptr(st) + p.aux_off + (size_t)C * sizeof(T)); };
