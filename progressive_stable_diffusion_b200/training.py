@@ -484,6 +484,9 @@ class DataParallelTrainer:
         self._graph = None
         self._reduce_after_backward = False      # capture() with world > 1: the graph holds forward + backward, the all-reduces follow it
         self._skip_allreduce = False             # measurement aid (bench: exposed share of the collective)
+        self._capture_events = None              # [(bucket, external event)] in completion order, filled while capturing
+        self.overlap_reduce = True               # captured data-parallel step: all-reduce buckets behind their events (else after the graph)
+        self._reduce_stream = None
 
     # ------------------------------------------------------------------ backward-time hooks
     def _on_grad(self, p: nn.Parameter) -> None:
@@ -494,8 +497,15 @@ class DataParallelTrainer:
             slot.copy_(p.grad.reshape(slot.shape))
             p.grad = slot
         bk.pending -= 1
-        if bk.pending == 0 and self.world > 1 and not self._reduce_after_backward:
-            bk.work = dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        if bk.pending == 0 and self.world > 1:
+            if not self._reduce_after_backward:
+                bk.work = dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            elif self._capture_events is not None:
+                # capturing forward + backward: mark "this bucket is complete" with an EXTERNAL event-record node; after every
+                # replay a side stream waits for it and starts the bucket's all-reduce while the graph is still in backward
+                ev = torch.cuda.Event(external=True)
+                ev.record()
+                self._capture_events.append((bk, ev))
 
     def zero_grad(self) -> None:
         for bk in self.buckets:
@@ -657,8 +667,9 @@ class DataParallelTrainer:
           * one process (world size 1): ONE graph holds gradient-bucket zeroing, forward, backward, clip and AdamW;
           * data parallel: the graph holds zeroing + forward + backward; ``replay`` then all-reduces the buckets (NCCL, eager: a
             capture that includes the hook-launched all-reduces deadlocked against ProcessGroupNCCL's watchdog on this stack,
-            torch 2.11 / NCCL 2.28) and runs the fused clip + AdamW kernels.  The collective is no longer hidden under backward,
-            but the step is still shorter than the host-bound eager one (bench ``config3``).
+            torch 2.11 / NCCL 2.28) and runs the fused clip + AdamW kernels.  The hooks leave an external event-record node
+            behind every completed bucket; ``replay`` makes a side stream wait for each event and start that bucket's all-reduce,
+            so the collectives still run under the rest of the captured backward (``overlap_reduce = False``: after the graph).
         ``loss_fn`` must read its inputs from tensors that keep their address (copy each batch into them before ``replay()``) and
         draw its random numbers from the default CUDA generator or from ``generators`` (registered with the graph).  ``warmup``
         eager steps run first (they are real optimizer steps): cuDNN / cuBLAS plans, the allocator, NCCL.  The step number and the
@@ -683,6 +694,7 @@ class DataParallelTrainer:
         ema_decay, self.ema_decay = self.ema_decay, None      # the host-side EMA decision stays out of the captured step
         steps_before = self.steps
         self._reduce_after_backward = not whole
+        self._capture_events = [] if not whole else None
         if not whole:                                 # no collective in flight while capturing (ProcessGroupNCCL's watchdog polls events)
             dist.barrier(group=self.pg)
             torch.cuda.synchronize(dev)
@@ -699,6 +711,10 @@ class DataParallelTrainer:
             self.ema_decay = ema_decay
             self.steps = steps_before                 # capturing executes nothing: the step is counted when it is replayed
         self._graph, self._graph_loss = graph, loss
+        events, self._capture_events = self._capture_events, None
+        if not whole:
+            assert len(events) == len(self.buckets), "a gradient bucket never completed during the captured backward"
+            self._reduce_stream = torch.cuda.Stream(device=dev)
 
         def replay() -> torch.Tensor:
             graph.replay()
@@ -709,7 +725,14 @@ class DataParallelTrainer:
                     self.ema_update()
             else:
                 if not self._skip_allreduce:
-                    works = [dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for bk in self.buckets]
+                    works = []
+                    if self.overlap_reduce:
+                        for bk, ev in events:         # completion order of the captured backward
+                            self._reduce_stream.wait_event(ev)
+                            with torch.cuda.stream(self._reduce_stream):
+                                works.append(dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                    else:
+                        works = [dist.all_reduce(bk.flat_g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for bk in self.buckets]
                     for w in works:
                         w.wait()
                 self.optimizer_step()                 # (eager: ~90 launches; counts the step, clears caches, EMA)

@@ -38,7 +38,47 @@ replay = trainer.capture(fn, generators=(gt,))
 if rank == 0:
     print("captured", flush=True)
 replay()
-ms_graph, l1 = timed(replay)
+
+
+def snapshot():
+    return [(bk.flat_p.clone(), bk.m.clone(), bk.v.clone()) for bk in trainer.buckets], trainer.dev_state.clone(), trainer.steps
+
+
+def restore(snap):
+    for bk, (p_, m_, v_) in zip(trainer.buckets, snap[0]):
+        bk.flat_p.copy_(p_); bk.m.copy_(m_); bk.v.copy_(v_)
+    trainer.dev_state.copy_(snap[1]); trainer.steps = snap[2]
+
+
+probe = [trainer.buckets[i] for i in (0, len(trainer.buckets) // 3, 2 * len(trainer.buckets) // 3, len(trainer.buckets) - 1)]
+grads = []
+
+
+def run(n):      # fixed generator state -> the same draws in both modes; the reduced gradients of the first step are kept
+    gt.manual_seed(1234 + rank)
+    out = []
+    for i in range(n):
+        out.append(replay().item())
+        if i == 0:
+            grads.append([bk.flat_g.clone() for bk in probe])
+    return out
+
+
+snap = snapshot()
+trainer.overlap_reduce = False
+la0 = run(3)                      # control: the same mode twice (cuDNN wgrad / reductions are not bit-reproducible run to run)
+restore(snap)
+la = run(3)
+wa = trainer.buckets[0].flat_p.clone()
+restore(snap)
+trainer.overlap_reduce = True
+lb = run(3)
+wb = trainer.buckets[0].flat_p.clone()
+same_modes = la == lb and torch.equal(wa, wb)
+ms_overlap, l1 = timed(replay)
+trainer.overlap_reduce = False
+ms_after, _ = timed(replay)
+trainer.overlap_reduce = True
 w = dict(module.named_parameters())["unet.unet.conv_in.weight"].detach().float()
 chk = [torch.zeros_like(w) for _ in range(world)]
 dist.all_gather(chk, w)
@@ -46,6 +86,14 @@ same = all(torch.equal(chk[0], c) for c in chk)
 trainer._skip_allreduce = True
 ms_off, _ = timed(replay)
 trainer._skip_allreduce = False
+def gdiff(a, b):
+    return max(((x - y).abs().max() / x.abs().max().clamp_min(1e-30)).item() for x, y in zip(a, b))
+
+
 if rank == 0:
-    print(f"world {world}: graphed {ms_graph:.1f} ms per step (without the all-reduce {ms_off:.1f}), loss {l1.item():.4f}, replicas identical after the graphed steps: {same}", flush=True)
+    print(f"reduced gradients of step 1, max |diff| / max |g| over 4 probe buckets: after-graph vs after-graph again {gdiff(grads[0], grads[1]):.3e}, "
+          f"after-graph vs behind-events {gdiff(grads[1], grads[2]):.3e}", flush=True)
+    print(f"world {world}: graphed {ms_overlap:.1f} ms per step with the all-reduces behind their bucket events, {ms_after:.1f} with the "
+          f"all-reduces after the graph, {ms_off:.1f} without them; losses after-graph {la0} / again {la} / behind events {lb}: bit-identical {same_modes}; "
+          f"replicas identical {same}", flush=True)
 dist.destroy_process_group()
