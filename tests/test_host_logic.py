@@ -228,3 +228,34 @@ def test_binding_refuses_a_library_of_another_abi(monkeypatch):
     monkeypatch.setattr(_lib, "ABI_VERSION", _lib.ABI_VERSION + 1)
     with pytest.raises(_lib.DaddError, match="ABI version"):
         _lib.load()
+
+
+def test_i12_progression_shares_one_noise_tensor_and_the_sweep_draws_independent_noise(module, monkeypatch):
+    """I12: all MES levels of a progression start from ONE noise tensor (inference_pipeline_ip.py:377-385), the evaluation sweep
+    draws independent noise per job from one seeded stream (evaluation_pipeline.py:506,909) - and a sharded sweep hands every job
+    the noise the single-process run gives it."""
+    from progressive_stable_diffusion_b200 import evaluation_pipeline as ev, inference_pipeline_ip as ip
+    seen = {}
+
+    def fake_sample(mod, target, source, images, latents, *a, **k):
+        seen["latents"] = latents
+        return latents
+
+    monkeypatch.setattr(ip, "_sample", fake_sample)
+    noise = torch.randn(1, 4, 32, 32)
+    tgt = ip._build_labels(13, 0.0, 3.0, "cpu")
+    ip._ddim_sample_ip(module, tgt, torch.zeros(13), torch.zeros(13, 16, 768), 50, "cpu", init_latents=noise)
+    lat = seen["latents"]
+    assert lat.shape == (13, 4, 32, 32) and all(torch.equal(lat[i], noise[0]) for i in range(13))
+
+    monkeypatch.setattr(ev, "_ddim_sample_batched", lambda mod, tgt, src, tok, steps, dev, eta, isc, ssc, gsc, init_latents=None: init_latents)
+    jobs = [(i % 5, float(i % 4), float((i + 1) % 4)) for i in range(29)]
+    tokens = torch.zeros(5, 16, 768)
+    single = ev.generate_all(module, jobs, tokens, "cpu", batch_size=4, sampling_steps=3, seed=7, decode=False)
+    assert sorted(single) == list(range(29))
+    assert len({single[i].flatten()[:8].numpy().tobytes() for i in single}) == 29          # independent draws
+    merged = {}
+    for rank in range(3):
+        merged.update(ev.generate_all(module, jobs, tokens, "cpu", batch_size=4, sampling_steps=3, seed=7, rank=rank, world_size=3,
+                                      decode=False))
+    assert sorted(merged) == list(range(29)) and all(torch.equal(merged[i], single[i]) for i in single)

@@ -28,6 +28,18 @@ def test_i11_fused_form_equals_three_pathways():
     torch.testing.assert_close(p @ torch.cat(vs, 2), ref, atol=2e-6, rtol=1e-5)
 
 
+def test_i10_baseline_frequency_reweighting_is_plain_softmax_attention():
+    """I10 (attention_processor_base.py:29-37,103-116): every frequency mode multiplies the probabilities by all-ones scales and
+    renormalises - the processor equals plain softmax attention up to that one extra rounding."""
+    for case in (c for c in cases.PROCESSOR_CASES if c["kind"] == "base"):
+        w, x, ehs = cases.processor_inputs(case)
+        with torch.no_grad():
+            both = processors.ordinal_ip_attention(w, x, ehs, "both")
+            for mode in ("aoe_dominant", "image_dominant", "both"):
+                got = processors.ordinal_ip_attention(w, x, ehs, mode)
+                torch.testing.assert_close(got, both, atol=2e-6 * both.abs().max().item(), rtol=0)
+
+
 def test_i8_i9_label_handling():
     w = weights.make_aoe_state(seed=23)
     lab = torch.tensor([-1.0, 0.0, 1.0, 2.5, 3.0, 7.0])
