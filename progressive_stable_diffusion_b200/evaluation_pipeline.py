@@ -1,12 +1,14 @@
 """Batched evaluation sampling for B200: the sampling half of
 ``/root/reference/src/pipelines/evaluation/evaluation_pipeline.py`` (``_prepare_conditioning`` :406-461,
-``_set_delta_scale`` :464-468, ``_ddim_sample_batched`` :471-564, ``_decode_latents`` :567-574, job batching of
-``generate_all`` :867-975).  The FID / CMMD / P&R metrics of that file use third-party backbones and are not on the
+``_set_delta_scale`` :464-468, ``_ddim_sample_batched`` :471-564, ``_decode_latents`` :567-574, ``GenerationJob`` / ``_collect_jobs``
+:83-89,843-864, the job order, batching and per-class grouping of ``generate_all`` :867-975).  The FID / CMMD / P&R metrics of that file use third-party backbones and are not on the
 denoising path.
 """
 
 from __future__ import annotations
 
+from dataclasses import dataclass
+from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -15,6 +17,64 @@ from torch import Tensor
 from . import parallel
 from .inference_pipeline_ip import (_latents_to_images, _prepare_conditioning as _prep, _sample,
                                     _set_delta_scale_on_processors)
+
+
+ALL_MES_CLASSES = [0, 1, 2, 3]                                                   # reference :79
+IMAGE_EXTENSIONS = {".bmp", ".png", ".jpg", ".jpeg", ".tif", ".tiff"}            # reference :80
+
+
+@dataclass
+class GenerationJob:
+    """One source image -> one target MES class (reference :83-89)."""
+
+    source_path: Path
+    source_label: int
+    target_label: int
+
+
+def _collect_jobs(data_roots: Sequence[Path], max_per_class: int = 0) -> List[GenerationJob]:
+    """Every source image under ``<root>/<class>/`` produces one job for each of the three OTHER MES classes, roots and classes
+    in order, files sorted, at most ``max_per_class`` files per class directory (reference :843-864)."""
+    jobs: List[GenerationJob] = []
+    for data_root in data_roots:
+        for cls in ALL_MES_CLASSES:
+            cls_dir = Path(data_root) / str(cls)
+            if not cls_dir.is_dir():
+                continue
+            paths = sorted(q for q in cls_dir.iterdir() if q.suffix.lower() in IMAGE_EXTENSIONS)
+            if max_per_class > 0:
+                paths = paths[:max_per_class]
+            for q in paths:
+                jobs.extend(GenerationJob(q, cls, target) for target in ALL_MES_CLASSES if target != cls)
+    return jobs
+
+
+def sweep_order(jobs: Sequence[GenerationJob]) -> Tuple[List[GenerationJob], List[Path]]:
+    """The order ``generate_all`` of the reference walks the jobs in (:897-903): sorted by (str(source path), target label), i.e.
+    grouped by source image.  Returns the sorted jobs and the distinct source paths in first-appearance order (the structure
+    images to load / encode ONCE each: the reference re-loads one per batch, :921-933)."""
+    jobs_sorted = sorted(jobs, key=lambda j: (str(j.source_path), j.target_label))
+    sources: List[Path] = []
+    for j in jobs_sorted:
+        if not sources or sources[-1] != j.source_path:
+            sources.append(j.source_path)
+    return jobs_sorted, sources
+
+
+def as_index_jobs(jobs_sorted: Sequence[GenerationJob], sources: Sequence[Path]) -> List[Tuple[int, float, float]]:
+    """``GenerationJob``s -> the (source index, source label, target label) triples ``generate_all`` below takes."""
+    where = {q: i for i, q in enumerate(sources)}
+    return [(where[j.source_path], float(j.source_label), float(j.target_label)) for j in jobs_sorted]
+
+
+def group_by_target(images: Dict[int, Tensor], jobs_sorted: Sequence[GenerationJob], image_size: int) -> Dict[int, Tensor]:
+    """Per-job images -> ``{target class: (N, 3, H, W)}`` in sweep order, empty classes as (0, 3, H, W): what the reference's
+    ``generate_all`` returns (:955-975).  ``images``: job index -> (3, H, W) (this rank's share, or all ranks' merged)."""
+    out: Dict[int, Tensor] = {}
+    for cls in ALL_MES_CLASSES:
+        picked = [images[i][None] for i, j in enumerate(jobs_sorted) if j.target_label == cls and i in images]
+        out[cls] = torch.cat(picked, dim=0) if picked else torch.zeros(0, 3, image_size, image_size)
+    return out
 
 
 def _prepare_conditioning(module, target_labels: Tensor, source_labels: Tensor, structure_images: Tensor,

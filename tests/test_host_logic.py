@@ -259,3 +259,32 @@ def test_i12_progression_shares_one_noise_tensor_and_the_sweep_draws_independent
         merged.update(ev.generate_all(module, jobs, tokens, "cpu", batch_size=4, sampling_steps=3, seed=7, rank=rank, world_size=3,
                                       decode=False))
     assert sorted(merged) == list(range(29)) and all(torch.equal(merged[i], single[i]) for i in single)
+
+
+def test_evaluation_sweep_jobs_follow_the_reference_order(tmp_path):
+    """``_collect_jobs`` / ``sweep_order`` / ``group_by_target``: the reference's job list (evaluation_pipeline.py:843-864), its
+    walk order (:897-903: sorted by (str(path), target)) and its per-class result layout (:955-975)."""
+    from progressive_stable_diffusion_b200 import evaluation_pipeline as ev
+    roots = [tmp_path / "a", tmp_path / "b"]
+    names = {"a": {0: ["z.png", "b.PNG", "notes.txt"], 2: ["m.jpg"]}, "b": {1: ["k.tif", "c.bmp", "d.png"], 3: []}}
+    for r, classes in names.items():
+        for cls, files in classes.items():
+            (tmp_path / r / str(cls)).mkdir(parents=True)
+            for f in files:
+                (tmp_path / r / str(cls) / f).write_bytes(b"")
+    jobs = ev._collect_jobs(roots, max_per_class=2)
+    # root a: class 0 -> b.PNG, z.png (sorted, the .txt is skipped); class 2 -> m.jpg; root b: class 1 -> c.bmp, d.png (k.tif cut by the cap)
+    assert [(j.source_path.name, j.source_label, j.target_label) for j in jobs] == [
+        ("b.PNG", 0, 1), ("b.PNG", 0, 2), ("b.PNG", 0, 3), ("z.png", 0, 1), ("z.png", 0, 2), ("z.png", 0, 3),
+        ("m.jpg", 2, 0), ("m.jpg", 2, 1), ("m.jpg", 2, 3), ("c.bmp", 1, 0), ("c.bmp", 1, 2), ("c.bmp", 1, 3),
+        ("d.png", 1, 0), ("d.png", 1, 2), ("d.png", 1, 3)]
+    jobs_sorted, sources = ev.sweep_order(list(reversed(jobs)))
+    assert jobs_sorted == sorted(jobs, key=lambda j: (str(j.source_path), j.target_label))
+    assert [q.name for q in sources] == ["b.PNG", "z.png", "m.jpg", "c.bmp", "d.png"] and len(set(sources)) == 5
+    idx = ev.as_index_jobs(jobs_sorted, sources)
+    assert idx[:4] == [(0, 0.0, 1.0), (0, 0.0, 2.0), (0, 0.0, 3.0), (1, 0.0, 1.0)] and len(idx) == 15
+    images = {i: torch.full((3, 8, 8), float(i)) for i in range(15)}
+    by_cls = ev.group_by_target(images, jobs_sorted, 8)
+    assert [by_cls[c].shape[0] for c in ev.ALL_MES_CLASSES] == [3, 3, 4, 5]
+    assert by_cls[0][:, 0, 0, 0].tolist() == [float(i) for i, j in enumerate(jobs_sorted) if j.target_label == 0]
+    assert ev.group_by_target({}, jobs_sorted, 8)[2].shape == (0, 3, 8, 8)
