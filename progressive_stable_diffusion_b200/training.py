@@ -710,6 +710,7 @@ class DataParallelTrainer:
         finally:
             self.ema_decay = ema_decay
             self.steps = steps_before                 # capturing executes nothing: the step is counted when it is replayed
+            self._reduce_after_backward = False       # (hooks do not run on replay; an eager step() after this reduces as before)
         self._graph, self._graph_loss = graph, loss
         events, self._capture_events = self._capture_events, None
         if not whole:
