@@ -616,7 +616,8 @@ class DataParallelTrainer:
         """The dictionary Lightning + the EMA callback write (ema_callback.py:291-330): ``state_dict`` = averaged weights (what
         ``load_from_checkpoint`` and the inference / evaluation pipelines read), ``current_model_state`` = the weights training
         continues from, ``averaging_state`` = AveragedModel's own entries (``n_averaged``), the callback's ``latest_update_step``
-        and the optimizer moments per bucket.  Without EMA: ``state_dict`` = the current weights."""
+        and the optimizer moments per bucket (bucket order: resume with the same ``bucket_bytes`` / parameter groups).  Without
+        EMA: ``state_dict`` = the current weights."""
         cur = {k: v.detach().clone() for k, v in self.module.state_dict().items()}
         ck = {"epoch": int(epoch), "global_step": int(self.steps), "state_dict": cur,
               "optimizer_moments": [None if bk.m is None else (bk.m.clone(), bk.v.clone()) for bk in self.buckets]}
@@ -674,7 +675,8 @@ class DataParallelTrainer:
         draw its random numbers from the default CUDA generator or from ``generators`` (registered with the graph).  ``warmup``
         eager steps run first (they are real optimizer steps): cuDNN / cuBLAS plans, the allocator, NCCL.  The step number and the
         learning-rate scale live on the device (``dadd_adamw_step_dev``); EMA updates are issued by ``replay`` on the reference
-        callback's schedule.  All ranks must capture and replay together."""
+        callback's schedule.  All ranks must capture and replay together.  The tensor ``replay`` returns is the graph's own loss
+        buffer: the next replay overwrites it (``.item()`` / ``.clone()`` it to keep a value)."""
         assert self.optimizer == "fused" and self.dev_state is not None, "graph capture needs the fused CUDA optimizer"
         dev = self.buckets[0].flat_p.device
         side = torch.cuda.Stream(device=dev)
