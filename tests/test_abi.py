@@ -80,6 +80,10 @@ def test_argument_validation_of_the_newer_entry_points(lib):
     assert l.dadd_ff_geglu_fwd(16, 16, 16, 16, 128, 320, 1280, 0, None) != 0 and "dtype16_ok" in err()      # fp32 not taken
     assert l.dadd_self_attn_fwd(16, 16, 16, 600, 600, 600, 16, 200, 1, 1, 64, 200, 0.1, 1, 0, None) != 0 and "wide" in err()   # d = 200
     assert l.dadd_groupnorm_select(1) == 0 and l.dadd_groupnorm_select(0) == 1
+    assert l.dadd_ema_update(None, 16, 64, 0.999, 0, None) != 0 and "dadd_ema_update" in err()
+    assert l.dadd_ema_update(16, 16, 64, 1.5, 0, None) != 0 and "decay" in err()
+    assert l.dadd_ema_update(16, 24, 64, 0.9, 0, None) != 0                                           # 16-byte alignment
+    assert l.dadd_adamw_step_dev(16, 16, 16, 16, 64, 1e-4, 0.9, 0.999, 1e-8, 0.01, None, None, None) != 0 and "dev_state" in err()
     assert l.dadd_groupnorm_cat_supported(4, 640, 320, 1024, 32, 1) == 1
     assert l.dadd_groupnorm_cat_supported(4, 644, 320, 1024, 32, 1) == 0    # C1 % 8
     assert l.dadd_groupnorm_cat_supported(4, 640, 320, 1024, 32, 0) == 0    # fp32
