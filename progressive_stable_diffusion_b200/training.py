@@ -719,6 +719,8 @@ class DataParallelTrainer:
             assert len(events) == len(self.buckets), "a gradient bucket never completed during the captured backward"
             self._reduce_stream = torch.cuda.Stream(device=dev)
 
+        self._replays = 0
+
         def replay() -> torch.Tensor:
             graph.replay()
             if whole:
@@ -729,7 +731,8 @@ class DataParallelTrainer:
             else:
                 if not self._skip_allreduce:
                     works = []
-                    if self.overlap_reduce:
+                    # (the first replay reduces after the graph: its event nodes have never been recorded before this launch)
+                    if self.overlap_reduce and self._replays > 0:
                         for bk, ev in events:         # completion order of the captured backward
                             self._reduce_stream.wait_event(ev)
                             with torch.cuda.stream(self._reduce_stream):
@@ -739,6 +742,7 @@ class DataParallelTrainer:
                     for w in works:
                         w.wait()
                 self.optimizer_step()                 # (eager: ~90 launches; counts the step, clears caches, EMA)
+            self._replays += 1
             return self._graph_loss
 
         return replay
