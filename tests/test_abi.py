@@ -94,3 +94,38 @@ def test_argument_validation_of_the_newer_entry_points(lib):
     assert l.dadd_cross_attn_fwd(16, 320, 16, 16, 16, 320, 1, 8, 64, 40, 16, 3, 16, 0.1, 1, 2, None) != 0 and "impl = 2" in err()
     assert l.dadd_add_layernorm_fwd(16, 16, None, 16, 16, 16, 16, 4, 320, 1e-5, 1, None) != 0            # sum_bias without sum_out
     assert l.dadd_purifier_attn_fwd(16, 16, 16, 16, 1, 16, 100000, 768, 8, None) != 0 and "shared memory" in err()
+
+
+def test_shipped_library_is_blackwell_native(lib):
+    """The hot kernels of the built library carry the sm_100a instructions the design claims (cuobjdump -sass, no GPU needed):
+    tcgen05 MMAs (UTCHMMA) with TMEM loads / stores and TMA tensor loads / stores in the self- and cross-attention cores, the
+    feed-forward GEGLU GEMM and the linear GEMM (whose CTA-pair form adds `.2CTA` MMAs), and no kernel built for another arch."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib.load()
+    sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "arch = sm_100a" in sass
+    per = {}
+    name, arch = None, None
+    for line in sass.splitlines():
+        a = re.search(r"arch = (sm_\w+)", line)
+        if a:
+            arch = a.group(1)
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            assert arch == "sm_100a", (m.group(1), arch)      # (the link step's empty default-arch stub holds no function)
+            name = m.group(1)
+            per[name] = line[:0]
+            continue
+        if name and re.search(r"UTCHMMA|UTMALDG|UTMASTG|LDTM|STTM|UBLKCP", line):
+            per[name] += re.search(r"(UTCHMMA(\.2CTA)?|UTMALDG|UTMASTG|LDTM|STTM|UBLKCP)", line).group(1) + " "
+    def kernels(tag):
+        return [v for k, v in per.items() if tag in k]
+    for tag in ("self_attn_tc_kernel", "cross_attn_tc_kernel", "ff_geglu_kernel", "linear_kernel"):
+        ks = kernels(tag)
+        assert ks and all("UTCHMMA" in v and "UTMALDG" in v and "LDTM" in v for v in ks), tag
+    assert any("UTCHMMA.2CTA" in v for v in kernels("linear_kernel")), "the CTA-pair linear GEMM lost its cta_group::2 MMAs"
+    assert all("STTM" in v for v in kernels("self_attn_tc_kernel")) and all("UTMASTG" in v for v in kernels("ff_geglu_kernel"))
+    assert all("UTMALDG" in v and "UTMASTG" in v for v in kernels("gn_stream_kernel")) and kernels("gn_cluster_kernel")
